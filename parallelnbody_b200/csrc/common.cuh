@@ -1,0 +1,48 @@
+// Shared helpers for the sm_100a kernels and the host runtime (no torch, no Unreal types).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace nbody {
+
+// Thread-local error string behind nbody_last_error().
+void set_error(const std::string& msg);
+
+struct Status {
+  int code;
+  explicit operator bool() const { return code == 0; }
+};
+
+#define NB_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      ::nbody::set_error(std::string("CUDA: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" +     \
+                         std::to_string(__LINE__) + " (" #expr ")");                                    \
+      return (_e == cudaErrorMemoryAllocation) ? -4 : -2;                                               \
+    }                                                                                                   \
+  } while (0)
+
+#define NB_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != 0) return _s;     \
+  } while (0)
+
+constexpr int kNumSMsB200 = 148;
+
+__host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Streaming 128-bit loads/stores for data touched once per kernel (keeps L1 for reused lines).
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace nbody

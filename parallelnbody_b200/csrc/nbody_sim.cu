@@ -1,0 +1,719 @@
+// Host runtime + C ABI (include/nbody.h) of the B200-native N-body hot path.
+//
+// `nbody_sim` is the device-resident counterpart of the reference's simulation actor, class AOctreeSearch
+// (/root/reference/Source/NBody/OctreeSearch.h:111-149, OctreeSearch.cpp:1-97): same verbs, but the bodies live
+// in HBM as float4 SoA (posm = x,y,z,mass | vel | acc), every step is a short sequence of kernel launches on one
+// stream with no host synchronisation in between, and the multi-GPU paths exchange data with NCCL.
+//
+// There is deliberately no CPU path in this file: if no sm_100 device is usable every entry point fails.
+#include "../../include/nbody.h"
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bh.cuh"
+#include "comm.h"
+#include "common.cuh"
+#include "direct_kernels.cuh"
+#include "integrate.cuh"
+
+namespace nbody {
+static thread_local std::string g_err;
+void set_error(const std::string& m) { g_err = m; }
+}  // namespace nbody
+
+using namespace nbody;
+
+namespace {
+
+int invalid(const std::string& m) { set_error(m); return NBODY_ERR_INVALID; }
+
+template <class T>
+int dev_reserve(T** p, int64_t* cap, int64_t need, cudaStream_t s) {
+  if (need <= *cap && *p) return 0;
+  if (*p) { NB_CUDA(cudaStreamSynchronize(s)); NB_CUDA(cudaFree(*p)); *p = nullptr; *cap = 0; }
+  const int64_t want = std::max<int64_t>(need, 256);
+  NB_CUDA(cudaMalloc((void**)p, (size_t)want * sizeof(T)));
+  *cap = want;
+  return 0;
+}
+
+struct DirectPlan {
+  int variant = 0;  // 0 = packed I=8 (1 CTA/SM), 1 = packed I=2 (3 CTAs/SM)
+  int i_per_thread = 8;
+  int n_itiles = 0, jsplit = 1, chunk = 0;
+  int64_t n_src_pad = 0, n_tgt_pad = 0;
+};
+
+DirectPlan plan_direct(int64_t n_tgt, int64_t n_src) {
+  DirectPlan p;
+  p.variant = n_tgt >= 32768 ? 0 : 1;
+  p.i_per_thread = p.variant == 0 ? 8 : 2;
+  const int itile = kDirectTPB * p.i_per_thread;
+  p.n_itiles = (int)ceil_div(n_tgt, itile);
+  // enough CTAs that the last partial wave is a few percent of the run, but chunks of >= 512 sources
+  const int64_t want_ctas = (int64_t)kNumSMsB200 * 48;
+  int js = 1;
+  while ((int64_t)p.n_itiles * js < want_ctas && js < 128 && ceil_div(n_src, js * 2) >= 512) js *= 2;
+  p.jsplit = js;
+  p.chunk = (int)round_up(ceil_div(n_src, js), kDirectTJ);
+  p.n_src_pad = (int64_t)p.chunk * js;
+  p.n_tgt_pad = round_up(n_tgt, 32);
+  return p;
+}
+
+}  // namespace
+
+struct nbody_sim {
+  nbody_config cfg;
+  bool initialized = false;
+  bool show_octree = false;
+  int64_t n_global = 0, n_local = 0, local_begin = 0, n_per = 0;
+  int64_t steps = 0;
+  double launches = 0;
+
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+
+  // state in HBM
+  float4* d_posm = nullptr;  int64_t cap_posm = 0;   // gathered sources (direct) / local bodies (BH)
+  float4* d_vel = nullptr;   int64_t cap_vel = 0;
+  float4* d_acc = nullptr;   int64_t cap_acc = 0;
+  float4* d_partial = nullptr; int64_t cap_partial = 0;
+  int32_t* d_ids = nullptr;  int64_t cap_ids = 0;     // original index of local body i (BH reorders bodies)
+  uint8_t* d_stage = nullptr; int64_t cap_stage = 0;
+  uint32_t* d_box = nullptr;   // 8 words: absmax, min xyz, max xyz
+  double* d_energy = nullptr;  // 2 doubles
+  bool ids_identity = true;
+
+  Comm* comm = nullptr;
+  DirectPlan plan;
+  BHState bh;
+
+  // timing of the last call
+  float ms_call = 0, ms_force = 0, ms_build = 0, ms_integrate = 0, ms_comm = 0;
+  double interactions = 0;
+  float cube_size = 0;
+
+  float4* posm_local() { return d_posm + (cfg.method == NBODY_DIRECT ? local_begin : 0); }
+};
+
+namespace {
+
+int check_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    set_error(std::string("CUDA: no usable device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    cudaGetLastError();
+    return NBODY_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) return invalid("device ordinal out of range");
+  cudaDeviceProp prop;
+  NB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("CUDA: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+              "; kernels are built for sm_100a only");
+    return NBODY_ERR_CUDA;
+  }
+  NB_CUDA(cudaSetDevice(device));
+  return 0;
+}
+
+cudaEvent_t pool_event(nbody_sim* s, size_t k) {
+  while (s->ev_pool.size() <= k) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    s->ev_pool.push_back(e);
+  }
+  return s->ev_pool[k];
+}
+
+// Split n bodies over the ranks: contiguous slices of n_per = ceil(n / world) (direct sum: fixed for the run).
+void partition(nbody_sim* s, int64_t n) {
+  s->n_global = n;
+  s->n_per = ceil_div(n, s->cfg.world);
+  s->local_begin = std::min<int64_t>(n, (int64_t)s->cfg.rank * s->n_per);
+  s->n_local = std::min<int64_t>(s->n_per, n - s->local_begin);
+}
+
+int reserve_state(nbody_sim* s) {
+  const int64_t n = s->n_global;
+  if (s->cfg.method == NBODY_DIRECT) {
+    s->plan = plan_direct(std::max<int64_t>(s->n_local, 1), s->n_per * s->cfg.world);
+    const int64_t need_src = std::max<int64_t>(s->plan.n_src_pad, s->n_per * s->cfg.world);
+    NB_TRY(dev_reserve(&s->d_posm, &s->cap_posm, need_src, s->stream));
+    NB_TRY(dev_reserve(&s->d_partial, &s->cap_partial, (int64_t)s->plan.jsplit * s->plan.n_tgt_pad, s->stream));
+  } else {
+    NB_TRY(dev_reserve(&s->d_posm, &s->cap_posm, std::max<int64_t>(s->n_local, 1), s->stream));
+  }
+  NB_TRY(dev_reserve(&s->d_vel, &s->cap_vel, std::max<int64_t>(s->n_local, 1), s->stream));
+  NB_TRY(dev_reserve(&s->d_acc, &s->cap_acc, std::max<int64_t>(s->n_local, 1), s->stream));
+  NB_TRY(dev_reserve(&s->d_ids, &s->cap_ids, std::max<int64_t>(s->n_local, 1), s->stream));
+  (void)n;
+  return 0;
+}
+
+// After the local slice of posm is in place: pad entries = zero-mass bodies at the origin, then make every rank's
+// slice visible everywhere (direct sum).
+int publish_positions(nbody_sim* s) {
+  if (s->cfg.method != NBODY_DIRECT) return 0;
+  const int64_t total = std::max<int64_t>(s->plan.n_src_pad, s->n_per * s->cfg.world);
+  // zero the tail of this rank's slot and everything past the real bodies
+  const int64_t slot_end = s->local_begin + s->n_per;
+  const int64_t pad0 = s->local_begin + s->n_local;
+  if (slot_end > pad0) {
+    fill_float4_kernel<<<(unsigned)ceil_div(slot_end - pad0, 256), 256, 0, s->stream>>>(s->d_posm + pad0, slot_end - pad0, make_float4(0, 0, 0, 0));
+    s->launches++;
+  }
+  const int64_t gathered = s->n_per * s->cfg.world;
+  if (total > gathered) {
+    fill_float4_kernel<<<(unsigned)ceil_div(total - gathered, 256), 256, 0, s->stream>>>(s->d_posm + gathered, total - gathered, make_float4(0, 0, 0, 0));
+    s->launches++;
+  }
+  NB_CUDA(cudaGetLastError());
+  if (s->comm) NB_TRY(s->comm->all_gather_f32_inplace(reinterpret_cast<float*>(s->d_posm), (size_t)s->n_per * 4, s->stream));
+  return 0;
+}
+
+template <int V, bool E0>
+void launch_direct_variant(const DirectPlan& p, const float4* src, const float4* tgt, int n_tgt, float eps2, float4* partial, cudaStream_t st) {
+  dim3 grid(p.n_itiles, p.jsplit);
+  if (V == 0) direct_packed_kernel<8, E0, 1><<<grid, kDirectTPB, 0, st>>>(src, p.chunk, tgt, n_tgt, eps2, partial, (int)p.n_tgt_pad);
+  else direct_packed_kernel<2, E0, 3><<<grid, kDirectTPB, 0, st>>>(src, p.chunk, tgt, n_tgt, eps2, partial, (int)p.n_tgt_pad);
+}
+
+int launch_direct(nbody_sim* s) {
+  if (s->n_local <= 0) return 0;
+  const float eps2 = s->cfg.eps * s->cfg.eps;
+  const float4* tgt = s->posm_local();
+  const bool e0 = !(eps2 > 0.f);
+  if (s->plan.variant == 0) {
+    if (e0) launch_direct_variant<0, true>(s->plan, s->d_posm, tgt, (int)s->n_local, eps2, s->d_partial, s->stream);
+    else launch_direct_variant<0, false>(s->plan, s->d_posm, tgt, (int)s->n_local, eps2, s->d_partial, s->stream);
+  } else {
+    if (e0) launch_direct_variant<1, true>(s->plan, s->d_posm, tgt, (int)s->n_local, eps2, s->d_partial, s->stream);
+    else launch_direct_variant<1, false>(s->plan, s->d_posm, tgt, (int)s->n_local, eps2, s->d_partial, s->stream);
+  }
+  s->launches++;
+  NB_CUDA(cudaGetLastError());
+  s->interactions = (double)s->n_local * (double)s->n_global;
+  return 0;
+}
+
+int launch_cube_size(nbody_sim* s) {
+  static const uint32_t init[8] = {0u, ~0u, ~0u, ~0u, 0u, 0u, 0u, 0u};
+  NB_CUDA(cudaMemcpyAsync(s->d_box, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+  if (s->n_local > 0) {
+    const int blocks = (int)std::min<int64_t>(ceil_div(s->n_local, 256), kNumSMsB200 * 8);
+    cube_size_kernel<<<blocks, 256, 0, s->stream>>>(s->posm_local(), (int)s->n_local, s->d_box);
+    s->launches++;
+    NB_CUDA(cudaGetLastError());
+  }
+  if (s->comm) {
+    NB_TRY(s->comm->all_reduce_u32_max(s->d_box, 1, s->stream));
+    NB_TRY(s->comm->all_reduce_u32_min(s->d_box + 1, 3, s->stream));
+    NB_TRY(s->comm->all_reduce_u32_max(s->d_box + 4, 3, s->stream));
+  }
+  return 0;
+}
+
+// One force evaluation (+ integration when dt > 0) enqueued on the stream. ev: optional 5 events
+// (start, after build, after force, after integrate, after comm).
+int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
+  if (ev) NB_CUDA(cudaEventRecord(ev[0], s->stream));
+  if (s->cfg.method == NBODY_DIRECT) {
+    if (ev) NB_CUDA(cudaEventRecord(ev[1], s->stream));
+    NB_TRY(launch_direct(s));
+    if (ev) NB_CUDA(cudaEventRecord(ev[2], s->stream));
+    if (s->n_local > 0) {
+      const unsigned blocks = (unsigned)ceil_div(s->n_local, 256);
+      if (integrate)
+        reduce_kick_drift_kernel<true><<<blocks, 256, 0, s->stream>>>(s->d_partial, s->plan.jsplit, s->plan.n_tgt_pad, (int)s->n_local, s->cfg.G, dt, s->posm_local(), s->d_vel, s->d_acc);
+      else
+        reduce_kick_drift_kernel<false><<<blocks, 256, 0, s->stream>>>(s->d_partial, s->plan.jsplit, s->plan.n_tgt_pad, (int)s->n_local, s->cfg.G, dt, s->posm_local(), s->d_vel, s->d_acc);
+      s->launches++;
+      NB_CUDA(cudaGetLastError());
+    }
+    if (ev) NB_CUDA(cudaEventRecord(ev[3], s->stream));
+    if (integrate && s->comm) NB_TRY(s->comm->all_gather_f32_inplace(reinterpret_cast<float*>(s->d_posm), (size_t)s->n_per * 4, s->stream));
+    if (ev) NB_CUDA(cudaEventRecord(ev[4], s->stream));
+  } else {
+    NB_TRY(launch_cube_size(s));   // OctreeSearch.cpp:26
+    BHParams bp;
+    bp.G = s->cfg.G; bp.eps2 = s->cfg.eps * s->cfg.eps; bp.theta = s->cfg.theta;
+    bp.leaf_size = std::max(1, s->cfg.leaf_size); bp.reference_root = s->cfg.reference_root != 0;
+    double launches = 0;
+    NB_TRY(bh_build(s->bh, bp, &s->d_posm, &s->d_vel, &s->d_ids, (int)s->n_local, s->d_box, s->stream, &launches));
+    s->ids_identity = false;
+    if (ev) NB_CUDA(cudaEventRecord(ev[1], s->stream));
+    NB_TRY(bh_forces(s->bh, bp, s->d_posm, s->d_acc, (int)s->n_local, s->stream, &launches));
+    s->launches += launches;
+    if (ev) NB_CUDA(cudaEventRecord(ev[2], s->stream));
+    if (integrate && s->n_local > 0) {
+      kick_drift_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>((int)s->n_local, dt, s->d_posm, s->d_vel, s->d_acc);
+      s->launches++;
+      NB_CUDA(cudaGetLastError());
+    }
+    if (ev) { NB_CUDA(cudaEventRecord(ev[3], s->stream)); NB_CUDA(cudaEventRecord(ev[4], s->stream)); }
+  }
+  if (integrate) s->steps++;
+  return 0;
+}
+
+int run_steps(nbody_sim* s, float dt, int nsteps, bool integrate, bool sync) {
+  if (!s->initialized) { set_error("not initialised: set bodies first (reference: Initialized == false)"); return NBODY_ERR_STATE; }
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  const int timed = sync ? std::min(nsteps, 128) : 0;
+  NB_CUDA(cudaEventRecord(s->ev0, s->stream));
+  for (int k = 0; k < nsteps; k++) {
+    cudaEvent_t ev[5];
+    bool use = k < timed;
+    if (use) for (int q = 0; q < 5; q++) { ev[q] = pool_event(s, (size_t)k * 5 + q); if (!ev[q]) use = false; }
+    NB_TRY(enqueue_step(s, dt, integrate, use ? ev : nullptr));
+  }
+  NB_CUDA(cudaEventRecord(s->ev1, s->stream));
+  if (!sync) return 0;
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  NB_CUDA(cudaEventElapsedTime(&s->ms_call, s->ev0, s->ev1));
+  s->ms_build = s->ms_force = s->ms_integrate = s->ms_comm = 0;
+  for (int k = 0; k < timed; k++) {
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEvent_t* e = &s->ev_pool[(size_t)k * 5];
+    NB_CUDA(cudaEventElapsedTime(&a, e[0], e[1]));
+    NB_CUDA(cudaEventElapsedTime(&b, e[1], e[2]));
+    NB_CUDA(cudaEventElapsedTime(&c, e[2], e[3]));
+    NB_CUDA(cudaEventElapsedTime(&d, e[3], e[4]));
+    s->ms_build += a; s->ms_force += b; s->ms_integrate += c; s->ms_comm += d;
+  }
+  if (timed > 0 && timed < nsteps) {  // scale the sampled phases to the whole call
+    const float f = (float)nsteps / (float)timed;
+    s->ms_build *= f; s->ms_force *= f; s->ms_integrate *= f; s->ms_comm *= f;
+  }
+  if (s->cfg.method == NBODY_BARNES_HUT) NB_TRY(bh_fetch_stats(s->bh, s->stream, &s->interactions));
+  return 0;
+}
+
+int stage_reserve(nbody_sim* s, int64_t bytes) { return dev_reserve(&s->d_stage, &s->cap_stage, bytes, s->stream); }
+
+int finish_set(nbody_sim* s) {
+  s->ids_identity = true;
+  if (s->cfg.method == NBODY_BARNES_HUT && s->n_local > 0) {
+    bh_iota(s->d_ids, (int)s->n_local, (int)s->local_begin, s->stream);
+    s->launches++;
+  }
+  bh_reset(s->bh);
+  NB_TRY(publish_positions(s));
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  s->initialized = true;
+  s->steps = 0;
+  return 0;
+}
+
+// Copies this rank's share back to the host at the bodies' original indices. what: 0 posm, 1 vel, 2 acc.
+int get_array(nbody_sim* s, int what, float* out4, int64_t n) {
+  if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
+  if (!out4 || n < s->n_global) return invalid("output buffer is NULL or smaller than n_global bodies");
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  const float4* src = what == 0 ? s->posm_local() : what == 1 ? s->d_vel : s->d_acc;
+  if (s->n_local == 0) return 0;
+  if (s->ids_identity) {
+    NB_CUDA(cudaMemcpyAsync(out4 + 4 * s->local_begin, src, (size_t)s->n_local * 16, cudaMemcpyDeviceToHost, s->stream));
+    NB_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+  }
+  std::vector<float4> tmp((size_t)s->n_local);
+  std::vector<int32_t> ids((size_t)s->n_local);
+  NB_CUDA(cudaMemcpyAsync(tmp.data(), src, (size_t)s->n_local * 16, cudaMemcpyDeviceToHost, s->stream));
+  NB_CUDA(cudaMemcpyAsync(ids.data(), s->d_ids, (size_t)s->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  for (int64_t i = 0; i < s->n_local; i++) memcpy(out4 + 4 * (size_t)ids[(size_t)i], &tmp[(size_t)i], 16);
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+extern "C" {
+
+int nbody_abi_version(void) { return NBODY_ABI_VERSION; }
+const char* nbody_last_error(void) { return g_err.c_str(); }
+
+int nbody_config_default(nbody_config* cfg) {
+  if (!cfg) return invalid("cfg is NULL");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = sizeof(nbody_config);
+  cfg->method = NBODY_BARNES_HUT;
+  cfg->G = 1e4f;
+  cfg->eps = 0.f;
+  cfg->theta = 1.0f;
+  cfg->ph_delta_time = 0.01f;
+  cfg->device = 0;
+  cfg->rank = 0;
+  cfg->world = 1;
+  cfg->leaf_size = 16;
+  cfg->reference_root = 0;
+  return NBODY_OK;
+}
+
+int nbody_comm_unique_id(uint8_t out128[128]) {
+  if (!out128) return invalid("out128 is NULL");
+  return Comm::unique_id(out128);
+}
+
+int nbody_create(nbody_sim** out, const nbody_config* cfg) {
+  if (!out || !cfg) return invalid("NULL argument");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(nbody_config)) return invalid("nbody_config.struct_size mismatch (use nbody_config_default)");
+  if (cfg->method != NBODY_DIRECT && cfg->method != NBODY_BARNES_HUT) return invalid("unknown method");
+  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return invalid("bad rank/world");
+  if (!(cfg->eps >= 0.f) || !(cfg->theta >= 0.f)) return invalid("eps and theta must be >= 0");
+  if (cfg->method == NBODY_BARNES_HUT && cfg->world > 1) return invalid("multi-GPU Barnes-Hut is not available in this build");
+  NB_TRY(check_device(cfg->device));
+  nbody_sim* s = new nbody_sim();
+  s->cfg = *cfg;
+  auto fail = [&](int code) { nbody_destroy(s); return code; };
+#define NB_C(expr) do { int _c = [&]() -> int { expr; return 0; }(); if (_c) return fail(_c); } while (0)
+  NB_C(if (cfg->stream) { s->stream = (cudaStream_t)cfg->stream; } else { NB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; });
+  NB_C(NB_CUDA(cudaEventCreate(&s->ev0)));
+  NB_C(NB_CUDA(cudaEventCreate(&s->ev1)));
+  NB_C(NB_CUDA(cudaMalloc((void**)&s->d_box, 8 * sizeof(uint32_t))));
+  NB_C(NB_CUDA(cudaMalloc((void**)&s->d_energy, 2 * sizeof(double))));
+  if (cfg->world > 1) NB_C(NB_TRY(Comm::create(&s->comm, cfg->nccl_unique_id, cfg->rank, cfg->world)));
+#undef NB_C
+  *out = s;
+  return NBODY_OK;
+}
+
+void nbody_destroy(nbody_sim* s) {
+  if (!s) return;
+  cudaSetDevice(s->cfg.device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  delete s->comm;
+  bh_free(s->bh);
+  cudaFree(s->d_posm); cudaFree(s->d_vel); cudaFree(s->d_acc); cudaFree(s->d_partial); cudaFree(s->d_ids);
+  cudaFree(s->d_stage); cudaFree(s->d_box); cudaFree(s->d_energy);
+  for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int nbody_create_space_points(nbody_sim* s, int64_t n, float size, uint64_t seed) {
+  if (!s) return invalid("sim is NULL");
+  if (n < 1 || n > (int64_t)1 << 30) return invalid("N must be in [1, 2^30] (the reference indexes Particles[0], OctreeSearch.cpp:68)");
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  partition(s, n);
+  NB_TRY(reserve_state(s));
+  if (s->n_local > 0) {
+    space_points_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(seed, s->local_begin, (int)s->n_local, size, s->posm_local(), s->d_vel, s->d_acc);
+    s->launches++;
+    NB_CUDA(cudaGetLastError());
+  }
+  s->cube_size = size;  // OctreeSearch.cpp:60
+  return finish_set(s);
+}
+
+int nbody_set_particles_aos(nbody_sim* s, const void* particles, int64_t n, size_t stride) {
+  if (!s) return invalid("sim is NULL");
+  if (n < 1 || n > (int64_t)1 << 30) return invalid("n must be in [1, 2^30]");
+  if (!particles) return invalid("particles is NULL");
+  if (stride < sizeof(nbody_particle) || stride % 4) return invalid("stride must be >= 40 and a multiple of 4");
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  partition(s, n);
+  NB_TRY(reserve_state(s));
+  if (s->n_local > 0) {
+    const size_t bytes = (size_t)s->n_local * stride;
+    NB_TRY(stage_reserve(s, (int64_t)bytes));
+    NB_CUDA(cudaMemcpyAsync(s->d_stage, (const uint8_t*)particles + (size_t)s->local_begin * stride, bytes, cudaMemcpyHostToDevice, s->stream));
+    aos_to_soa_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(s->d_stage, stride, 0, (int)s->n_local, s->posm_local(), s->d_vel, s->d_acc);
+    s->launches++;
+    NB_CUDA(cudaGetLastError());
+  }
+  return finish_set(s);
+}
+
+int nbody_set_bodies(nbody_sim* s, const float* posm4, const float* vel4, int64_t n) {
+  if (!s) return invalid("sim is NULL");
+  if (n < 1 || n > (int64_t)1 << 30) return invalid("n must be in [1, 2^30]");
+  if (!posm4) return invalid("posm4 is NULL");
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  partition(s, n);
+  NB_TRY(reserve_state(s));
+  if (s->n_local > 0) {
+    NB_CUDA(cudaMemcpyAsync(s->posm_local(), posm4 + 4 * s->local_begin, (size_t)s->n_local * 16, cudaMemcpyHostToDevice, s->stream));
+    if (vel4) NB_CUDA(cudaMemcpyAsync(s->d_vel, vel4 + 4 * s->local_begin, (size_t)s->n_local * 16, cudaMemcpyHostToDevice, s->stream));
+    else NB_CUDA(cudaMemsetAsync(s->d_vel, 0, (size_t)s->n_local * 16, s->stream));
+    NB_CUDA(cudaMemsetAsync(s->d_acc, 0, (size_t)s->n_local * 16, s->stream));
+  }
+  return finish_set(s);
+}
+
+int nbody_clean_particles(nbody_sim* s) {
+  if (!s) return invalid("sim is NULL");
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  s->initialized = false;  // OctreeSearch.cpp:93
+  s->n_global = s->n_local = 0;
+  s->steps = 0;
+  bh_reset(s->bh);
+  return NBODY_OK;
+}
+
+int nbody_compute_cube_size(nbody_sim* s, float* size_out) {
+  if (!s) return invalid("sim is NULL");
+  if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }  // OctreeSearch.cpp:49 returns silently
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  NB_TRY(launch_cube_size(s));
+  uint32_t bits = 0;
+  NB_CUDA(cudaMemcpyAsync(&bits, s->d_box, 4, cudaMemcpyDeviceToHost, s->stream));
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  memcpy(&s->cube_size, &bits, 4);
+  if (size_out) *size_out = s->cube_size;
+  return NBODY_OK;
+}
+
+int nbody_create_octree(nbody_sim* s) {
+  if (!s) return invalid("sim is NULL");
+  return run_steps(s, 0.f, 1, false, true);
+}
+
+int nbody_tick(nbody_sim* s) {
+  if (!s) return invalid("sim is NULL");
+  if (!(s->cfg.ph_delta_time > 0.f)) return NBODY_OK;  // OctreeSearch.cpp:25: paused
+  if (!s->initialized) return NBODY_OK;                // OctreeSearch.cpp:49,76: silently nothing to do
+  return run_steps(s, s->cfg.ph_delta_time, 1, true, true);
+}
+
+int nbody_step(nbody_sim* s, float dt, int32_t nsteps) {
+  if (!s) return invalid("sim is NULL");
+  if (nsteps < 0) return invalid("nsteps < 0");
+  if (!(dt > 0.f) || nsteps == 0) return NBODY_OK;
+  return run_steps(s, dt, nsteps, true, true);
+}
+
+int nbody_step_async(nbody_sim* s, float dt, int32_t nsteps) {
+  if (!s) return invalid("sim is NULL");
+  if (nsteps < 0) return invalid("nsteps < 0");
+  if (!(dt > 0.f) || nsteps == 0) return NBODY_OK;
+  return run_steps(s, dt, nsteps, true, false);
+}
+
+int nbody_synchronize(nbody_sim* s) {
+  if (!s) return invalid("sim is NULL");
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  return NBODY_OK;
+}
+
+int nbody_get_positions(nbody_sim* s, float* out, int64_t n) { return s ? get_array(s, 0, out, n) : invalid("sim is NULL"); }
+int nbody_get_velocities(nbody_sim* s, float* out, int64_t n) { return s ? get_array(s, 1, out, n) : invalid("sim is NULL"); }
+int nbody_get_accelerations(nbody_sim* s, float* out, int64_t n) { return s ? get_array(s, 2, out, n) : invalid("sim is NULL"); }
+
+int nbody_get_particles_aos(nbody_sim* s, void* particles, int64_t n, size_t stride) {
+  if (!s) return invalid("sim is NULL");
+  if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
+  if (!particles || n < s->n_global) return invalid("output buffer is NULL or smaller than n_global bodies");
+  if (stride < sizeof(nbody_particle) || stride % 4) return invalid("stride must be >= 40 and a multiple of 4");
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  if (s->n_local == 0) return NBODY_OK;
+  const size_t bytes = (size_t)s->n_local * 40;
+  NB_TRY(stage_reserve(s, (int64_t)bytes));
+  soa_to_aos_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(s->posm_local(), s->d_vel, s->d_acc, (int)s->n_local, reinterpret_cast<float*>(s->d_stage));
+  s->launches++;
+  NB_CUDA(cudaGetLastError());
+  uint8_t* dst = (uint8_t*)particles;
+  if (s->ids_identity && stride == 40) {
+    NB_CUDA(cudaMemcpyAsync(dst + (size_t)s->local_begin * 40, s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
+    NB_CUDA(cudaStreamSynchronize(s->stream));
+    return NBODY_OK;
+  }
+  std::vector<uint8_t> tmp(bytes);
+  std::vector<int32_t> ids;
+  NB_CUDA(cudaMemcpyAsync(tmp.data(), s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
+  if (!s->ids_identity) {
+    ids.resize((size_t)s->n_local);
+    NB_CUDA(cudaMemcpyAsync(ids.data(), s->d_ids, (size_t)s->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
+  }
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  for (int64_t i = 0; i < s->n_local; i++) {
+    const int64_t g = s->ids_identity ? s->local_begin + i : ids[(size_t)i];
+    memcpy(dst + (size_t)g * stride, tmp.data() + (size_t)i * 40, 40);
+  }
+  return NBODY_OK;
+}
+
+int nbody_get_local_ids(nbody_sim* s, int64_t* ids, int64_t cap, int64_t* n_local) {
+  if (!s) return invalid("sim is NULL");
+  if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
+  if (n_local) *n_local = s->n_local;
+  if (!ids) return NBODY_OK;
+  if (cap < s->n_local) return invalid("ids capacity too small");
+  if (s->ids_identity) {
+    for (int64_t i = 0; i < s->n_local; i++) ids[i] = s->local_begin + i;
+    return NBODY_OK;
+  }
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  std::vector<int32_t> h((size_t)s->n_local);
+  NB_CUDA(cudaMemcpyAsync(h.data(), s->d_ids, (size_t)s->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  for (int64_t i = 0; i < s->n_local; i++) ids[i] = h[(size_t)i];
+  return NBODY_OK;
+}
+
+int nbody_set_param(nbody_sim* s, int32_t which, double v) {
+  if (!s) return invalid("sim is NULL");
+  switch (which) {
+    case NBODY_PARAM_G: s->cfg.G = (float)v; return NBODY_OK;
+    case NBODY_PARAM_EPS: if (!(v >= 0)) return invalid("eps must be >= 0"); s->cfg.eps = (float)v; return NBODY_OK;
+    case NBODY_PARAM_THETA: if (!(v >= 0)) return invalid("theta must be >= 0"); s->cfg.theta = (float)v; return NBODY_OK;
+    case NBODY_PARAM_PH_DELTA_TIME: s->cfg.ph_delta_time = (float)v; return NBODY_OK;
+    case NBODY_PARAM_LEAF_SIZE: if (v < 1 || v > 64) return invalid("leaf_size must be in [1, 64]"); s->cfg.leaf_size = (int)v; return NBODY_OK;
+    case NBODY_PARAM_REFERENCE_ROOT: s->cfg.reference_root = v != 0; return NBODY_OK;
+    case NBODY_PARAM_SHOW_OCTREE: s->show_octree = v != 0; return NBODY_OK;
+    case NBODY_PARAM_METHOD: return invalid("method is fixed at nbody_create (device layout depends on it)");
+    default: return invalid("unknown or read-only parameter");
+  }
+}
+
+int nbody_get_param(nbody_sim* s, int32_t which, double* v) {
+  if (!s || !v) return invalid("NULL argument");
+  switch (which) {
+    case NBODY_PARAM_G: *v = s->cfg.G; return NBODY_OK;
+    case NBODY_PARAM_EPS: *v = s->cfg.eps; return NBODY_OK;
+    case NBODY_PARAM_THETA: *v = s->cfg.theta; return NBODY_OK;
+    case NBODY_PARAM_PH_DELTA_TIME: *v = s->cfg.ph_delta_time; return NBODY_OK;
+    case NBODY_PARAM_METHOD: *v = s->cfg.method; return NBODY_OK;
+    case NBODY_PARAM_LEAF_SIZE: *v = s->cfg.leaf_size; return NBODY_OK;
+    case NBODY_PARAM_REFERENCE_ROOT: *v = s->cfg.reference_root; return NBODY_OK;
+    case NBODY_PARAM_SHOW_OCTREE: *v = s->show_octree; return NBODY_OK;
+    case NBODY_PARAM_INITIALIZED: *v = s->initialized; return NBODY_OK;
+    default: return invalid("unknown parameter");
+  }
+}
+
+int nbody_energy(nbody_sim* s, double* ke, double* pe) {
+  if (!s) return invalid("sim is NULL");
+  if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  NB_CUDA(cudaMemsetAsync(s->d_energy, 0, 2 * sizeof(double), s->stream));
+  if (s->n_local > 0) {
+    const float4* src = s->d_posm;
+    const int n_src = (int)(s->cfg.method == NBODY_DIRECT ? s->n_global : s->n_local);
+    // global index of local body i for the self-pair exclusion: direct = slice offset; BH (single GPU, reordered
+    // bodies) = position in the local array, which is also its position in the source array.
+    const int64_t first = s->cfg.method == NBODY_DIRECT ? s->local_begin : 0;
+    energy_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(src, n_src, s->posm_local(), s->d_vel, (int)s->n_local, first, s->cfg.G, s->cfg.eps * s->cfg.eps, s->d_energy);
+    s->launches++;
+    NB_CUDA(cudaGetLastError());
+  }
+  if (s->comm) NB_TRY(s->comm->all_reduce_f64_sum(s->d_energy, 2, s->stream));
+  double h[2];
+  NB_CUDA(cudaMemcpyAsync(h, s->d_energy, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  if (ke) *ke = h[0];
+  if (pe) *pe = h[1];
+  return NBODY_OK;
+}
+
+int nbody_stats_get(nbody_sim* s, nbody_stats* out) {
+  if (!s || !out) return invalid("NULL argument");
+  memset(out, 0, sizeof(*out));
+  out->struct_size = sizeof(nbody_stats);
+  out->method = s->cfg.method;
+  out->n_global = s->n_global; out->n_local = s->n_local; out->steps = s->steps;
+  out->interactions = s->interactions; out->kernel_launches = s->launches;
+  out->ms_last_call = s->ms_call; out->ms_force = s->ms_force; out->ms_build = s->ms_build;
+  out->ms_integrate = s->ms_integrate; out->ms_comm = s->ms_comm;
+  out->cube_size = s->cube_size;
+  out->jsplit = s->plan.jsplit; out->i_per_thread = s->plan.i_per_thread;
+  out->tree_nodes = s->bh.n_nodes_host; out->tree_depth = s->bh.depth_host;
+  memcpy(out->root_com, s->bh.root_com_host, sizeof(out->root_com));
+  out->root_mass = s->bh.root_mass_host;
+  return NBODY_OK;
+}
+
+int nbody_octree_boxes(nbody_sim* s, float* boxes7, int64_t cap, int64_t* n_boxes) {
+  if (!s || !n_boxes) return invalid("NULL argument");
+  if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
+  if (s->cfg.method != NBODY_BARNES_HUT) return invalid("octree boxes exist only for the Barnes-Hut method");
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  return bh_leaf_boxes(s->bh, s->d_posm, (int)s->n_local, boxes7, cap, n_boxes, s->stream);
+}
+
+int nbody_device_ptrs(nbody_sim* s, void** posm4, void** vel4, void** acc4) {
+  if (!s) return invalid("sim is NULL");
+  if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
+  if (posm4) *posm4 = s->posm_local();
+  if (vel4) *vel4 = s->d_vel;
+  if (acc4) *acc4 = s->d_acc;
+  return NBODY_OK;
+}
+
+// ---- FP32 peak probe ----------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+// 16 independent FFMA chains per thread with register-only operands: the sustained FP32 issue rate.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, const float* in, int iters, long long* cyc) {
+  float acc[16], x[16], y[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) { acc[k] = in[k]; x[k] = in[16 + k] + threadIdx.x; y[k] = in[32 + k]; }
+  const long long c0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int k = 0; k < 16; k++) acc[k] = fmaf(x[k], y[(k + u) & 15], acc[k]);
+  }
+  const long long c1 = clock64();
+  float sum = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) sum += acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = c1 - c0;
+}
+}  // namespace
+
+extern "C" int nbody_measure_fp32_peak(int32_t device, double* tflops, double* sm_mhz) {
+  NB_TRY(check_device(device));
+  const int blocks = kNumSMsB200 * 4, iters = 40000;
+  float *d_out = nullptr, *d_in = nullptr;
+  long long* d_cyc = nullptr;
+  NB_CUDA(cudaMalloc((void**)&d_out, (size_t)blocks * 256 * 4));
+  NB_CUDA(cudaMalloc((void**)&d_in, 48 * 4));
+  NB_CUDA(cudaMalloc((void**)&d_cyc, (size_t)blocks * 8));
+  float h[48];
+  for (int i = 0; i < 48; i++) h[i] = 0.001f * (float)(i + 1);
+  NB_CUDA(cudaMemcpy(d_in, h, sizeof(h), cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  NB_CUDA(cudaEventCreate(&e0));
+  NB_CUDA(cudaEventCreate(&e1));
+  fp32_peak_kernel<<<blocks, 256>>>(d_out, d_in, iters / 4, d_cyc);
+  NB_CUDA(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < 5; r++) {
+    NB_CUDA(cudaEventRecord(e0));
+    fp32_peak_kernel<<<blocks, 256>>>(d_out, d_in, iters, d_cyc);
+    NB_CUDA(cudaEventRecord(e1));
+    NB_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    NB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  std::vector<long long> cyc((size_t)blocks);
+  NB_CUDA(cudaMemcpy(cyc.data(), d_cyc, (size_t)blocks * 8, cudaMemcpyDeviceToHost));
+  double cmax = 0;
+  for (long long c : cyc) cmax = std::max(cmax, (double)c);
+  const double fma = 128.0 * (double)iters * (double)blocks * 256.0;
+  if (tflops) *tflops = 2.0 * fma / ((double)best * 1e-3) * 1e-12;
+  if (sm_mhz) *sm_mhz = cmax / ((double)best * 1e-3) * 1e-6;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_out); cudaFree(d_in); cudaFree(d_cyc);
+  return NBODY_OK;
+}

@@ -1,0 +1,207 @@
+"""GPU parity tests for the direct-sum path (K1 + K2) through the C ABI, against the CPU oracle.
+
+Tolerances (BASELINE north_star): direct-sum accelerations within 1e-5 relative L2 of the fp64 restatement
+(the fp32 reference is shown alongside); integrator bit-exact given the same accelerations; 100-step
+trajectories agree with the reference-arithmetic CPU run to fp32 round-off growth and energy drift matches.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+ACC_TOL = 1e-5
+
+
+def _sim(**kw):
+    import parallelnbody_b200 as P
+    return P.OctreeSearch(method=P.METHOD_DIRECT, **kw)
+
+
+@pytest.mark.parametrize("n", [4096, 1, 2, 255, 257, 1000, 5000, 40000])
+def test_direct_acc_softened_vs_fp64(oracle, n):
+    from parallelnbody_b200 import ic
+    posm, vel = ic.plummer(n, seed=7)
+    with _sim(eps=0.01) as s:
+        s.SetBodies(posm, vel)
+        s.CreateOctree()
+        acc = s.Accelerations()
+    ref = oracle.direct_f64(posm, G=1e4, eps=0.01)
+    if n == 1:
+        assert np.all(acc == 0)
+        return
+    assert rel_l2(acc, ref) <= ACC_TOL
+    assert np.all(acc[:, 3] == 0)
+
+
+def test_direct_eps0_matches_reference_theta0_walk(oracle):
+    """eps = 0: the reference's own 'direct sum' is its walk at Theta = 0 (OctreeSearch.h:99-108)."""
+    from parallelnbody_b200 import ic
+    posm, vel = ic.reference_slab(3000, seed=11)
+    with _sim(eps=0.0) as s:
+        s.Particles = oracle.to_aos(posm, vel)
+        s.CreateOctree()
+        acc = s.Accelerations()
+    f64 = oracle.direct_f64(posm, G=1e4, eps=0.0)
+    assert rel_l2(acc, f64) <= ACC_TOL
+    if oracle.have_ref():
+        r = oracle.RefSim()
+        r.SetParticles(oracle.to_aos(posm, vel))
+        r.ComputeCubeSize(); r.CreateOctree(); r.ComputeForces(0.0)
+        a_ref = oracle.from_aos(r.Particles())[2]
+        # both are fp32 evaluations of the same sum in different orders
+        assert rel_l2(acc, a_ref) <= 2e-5
+        assert rel_l2(a_ref, f64) <= 2e-5
+
+
+def test_coincident_and_zero_mass_bodies(oracle):
+    """d == 0 pairs are skipped (OctreeSearch.h:102) - the reference's Add() would never return on these."""
+    rng = np.random.default_rng(3)
+    posm = rng.uniform(-1, 1, (600, 4)).astype(np.float32)
+    posm[:, 3] = 1e-3
+    posm[100] = posm[7]          # exactly coincident pair
+    posm[200, 3] = 0.0           # massless tracer
+    for eps in (0.0, 0.05):
+        with _sim(eps=eps) as s:
+            s.SetBodies(posm)
+            s.CreateOctree()
+            acc = s.Accelerations()
+        assert np.all(np.isfinite(acc))
+        assert rel_l2(acc, oracle.direct_f64(posm, eps=eps)) <= ACC_TOL
+
+
+def test_integrator_bit_exact_given_acc(oracle):
+    """K2 applies v += dt*a; x += dt*v exactly as OctreeSearch.cpp:28-31 (no FMA contraction)."""
+    from parallelnbody_b200 import ic
+    posm, vel = ic.plummer(2048, seed=5)
+    with _sim(eps=0.01) as s:
+        s.SetBodies(posm, vel)
+        s.Step(1e-3, 1)
+        p1, v1, a1 = s.Positions(), s.Velocities(), s.Accelerations()
+    p, v = posm.copy(), vel.copy()
+    oracle.kick_drift(p, v, a1, np.float32(1e-3))
+    assert np.array_equal(p, p1) and np.array_equal(v[:, :3], v1[:, :3])
+
+
+def test_config1_plummer4096_100_steps(oracle):
+    """BASELINE config 1: Plummer N=4096, softened direct sum, 100 kick-drift steps dt=1e-3."""
+    from parallelnbody_b200 import ic
+    n, dt, eps, steps = 4096, 1e-3, 0.01, 100
+    posm, vel = ic.plummer(n, seed=1234)
+    with _sim(eps=eps) as s:
+        s.SetBodies(posm, vel)
+        ke0, pe0 = s.Energy()
+        s.Step(dt, steps)
+        pg, vg = s.Positions(), s.Velocities()
+        ke1, pe1 = s.Energy()
+        assert s.Stats()["steps"] == steps
+    p, v, a = posm.copy(), vel.copy(), np.zeros_like(posm)
+    for _ in range(steps):
+        oracle.tick(p, v, a, dt, G=1e4, eps=eps, method=0)
+    oke0, ope0 = oracle.energy(posm, vel, 1e4, eps)
+    oke1, ope1 = oracle.energy(p, v, 1e4, eps)
+    # energies computed on device agree with the fp64 oracle
+    assert abs(ke0 - oke0) <= 1e-6 * abs(oke0) and abs(pe0 - ope0) <= 1e-5 * abs(ope0)
+    # trajectories: same integrator, accelerations equal to ~1e-6 -> positions agree far below the system scale
+    assert rel_l2(pg, p) <= 1e-5
+    assert rel_l2(vg, v) <= 1e-4
+    drift_gpu = abs((ke1 + pe1) - (ke0 + pe0)) / abs(ke0 + pe0)
+    drift_cpu = abs((oke1 + ope1) - (oke0 + ope0)) / abs(oke0 + ope0)
+    assert drift_gpu < 1e-3 and drift_cpu < 1e-3
+    assert abs(drift_gpu - drift_cpu) < 2e-5
+
+
+def test_config2_uniform65536_properties_and_subsample(oracle):
+    """BASELINE config 2 at full size: fp64 oracle on a 512-target subsample (all 65,536 sources) + momentum."""
+    from parallelnbody_b200 import ic
+    n = 65536
+    posm, vel = ic.uniform_cube(n, seed=1234)
+    with _sim(eps=0.01) as s:
+        s.SetBodies(posm, vel)
+        s.CreateOctree()
+        acc = s.Accelerations()
+        st = s.Stats()
+    assert st["interactions"] == float(n) * n
+    sub = oracle.direct_f64(posm, eps=0.01, i0=1000, i1=1512)
+    assert rel_l2(acc[1000:1512], sub) <= ACC_TOL
+    # Newton's third law: sum m_i a_i = 0 up to fp32 summation noise
+    f = (posm[:, 3:4].astype(np.float64) * acc[:, :3]).sum(0)
+    scale = np.abs(posm[:, 3:4].astype(np.float64) * acc[:, :3]).sum(0)
+    assert np.all(np.abs(f) <= 1e-5 * scale)
+
+
+def test_permutation_and_translation_invariance(oracle):
+    from parallelnbody_b200 import ic
+    posm, _ = ic.plummer(3000, seed=9)
+    perm = np.random.default_rng(1).permutation(3000)
+    with _sim(eps=0.02) as s:
+        s.SetBodies(posm); s.CreateOctree(); a0 = s.Accelerations()
+        s.SetBodies(posm[perm]); s.CreateOctree(); a1 = s.Accelerations()
+        shifted = posm.copy(); shifted[:, :3] += np.float32(0.5)
+        s.SetBodies(shifted); s.CreateOctree(); a2 = s.Accelerations()
+    assert rel_l2(a1, a0[perm]) <= 2e-6
+    assert rel_l2(a2, a0) <= 1e-5
+
+
+def test_aos_round_trip_and_lifecycle(oracle):
+    import parallelnbody_b200 as P
+    from parallelnbody_b200 import ic
+    posm, vel = ic.reference_slab(1234, seed=2)
+    aos = oracle.to_aos(posm, vel)
+    with _sim() as s:
+        assert not s.Initialized
+        s.Tick()            # not initialised: silently nothing (OctreeSearch.cpp:49,76)
+        s.CreateOctree()
+        s.Particles = aos
+        assert s.Initialized and s.Num() == 1234
+        back = s.Particles
+        assert np.array_equal(back["Position"], aos["Position"]) and np.array_equal(back["Velocity"], aos["Velocity"])
+        assert np.array_equal(back["Mass"], aos["Mass"])
+        assert abs(s.ComputeCubeSize() - oracle.cube_size(posm)) == 0.0
+        s.PhDeltaTime = 0.0   # paused (OctreeSearch.cpp:25)
+        s.Tick()
+        assert np.array_equal(s.Particles["Position"], aos["Position"])
+        s.PhDeltaTime = 0.01
+        s.Tick()
+        assert not np.array_equal(s.Particles["Position"], aos["Position"])
+        s.CleanParticles()
+        assert not s.Initialized and s.Num() == 0
+        with pytest.raises(P.NBodyError):
+            s.Step(0.01, 1)
+        s.Particles = aos[:100]
+        assert s.Num() == 100
+
+
+def test_create_space_points_law():
+    """Device generator follows AOctreeSearch::CreateSpacePoints (OctreeSearch.cpp:58-72)."""
+    with _sim() as s:
+        s.CreateSpacePoints(20000, 1000.0, seed=42)
+        p = s.Particles
+        assert s.Size == 1000.0
+    pos, vel, m = p["Position"], p["Velocity"], p["Mass"]
+    assert np.all(pos[0] == 0) and np.all(vel[0] == 0) and m[0] == 5000.0
+    assert np.abs(pos[:, 0]).max() <= 1000 and np.abs(pos[:, 1]).max() <= 1000 and np.abs(pos[:, 2]).max() <= 100
+    assert np.abs(pos[:, 0]).max() > 990 and np.abs(pos[:, 2]).max() > 99
+    sp = np.linalg.norm(vel[1:].astype(np.float64), axis=1)
+    assert np.allclose(sp / 10, np.round(sp / 10), atol=1e-3) and sp.min() >= 249.9 and sp.max() <= 500.1
+    assert np.all(m == np.round(m)) and m.min() >= 1 and m.max() <= 5000
+    assert abs(vel[1:].mean(0)).max() < 10     # isotropic
+    with _sim() as s2:
+        s2.CreateSpacePoints(20000, 1000.0, seed=42)
+        assert np.array_equal(s2.Particles["Position"], pos)    # seeded => reproducible
+
+
+def test_error_paths():
+    import parallelnbody_b200 as P
+    with pytest.raises(P.NBodyError):
+        P.OctreeSearch(method=7)
+    with pytest.raises(P.NBodyError):
+        P.OctreeSearch(method=P.METHOD_DIRECT, eps=-1.0)
+    with _sim() as s:
+        with pytest.raises(P.NBodyError):
+            s.CreateSpacePoints(0, 10.0)
+        with pytest.raises(P.NBodyError):
+            s.SetBodies(np.zeros((4, 3), np.float32))
+        with pytest.raises(P.NBodyError):
+            s.Accelerations() if s.Initialized else s.Step(1.0, 1)
