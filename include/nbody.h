@@ -67,7 +67,11 @@ typedef struct nbody_config {
   int32_t leaf_size;      /* Barnes-Hut: max bodies per leaf bucket (default 16; 1 = reference's one-body leaves) */
   int32_t reference_root; /* Barnes-Hut: 1 = root cube as the reference (origin = previous root COM, half-width =
                              max |coord|, OctreeSearch.cpp:47-56,77-79); 0 = tight cube around the bodies */
-  int32_t reserved[5];
+  int32_t mac;            /* Barnes-Hut acceptance test: 0 = per walk group of <= 64 neighbouring bodies (production: a cell
+                             is accepted when half-width / distance(group box, cell COM) < theta - never accepts what the
+                             reference's per-body test would open); 1 = per body, exactly OctreeSearch.h:100-107 incl. the
+                             visiting order (parity mode, slower) */
+  int32_t reserved[4];
   uint8_t nccl_unique_id[128]; /* multi-GPU: the ncclUniqueId from nbody_comm_unique_id on rank 0 */
   void* stream;           /* optional cudaStream_t to run on (NULL = the handle creates its own) */
 } nbody_config;
@@ -141,7 +145,8 @@ int nbody_synchronize(nbody_sim* sim);
 
 /* ---- bodies out (replaces reading Particles[i].Position/Velocity/Acceleration, OctreeSearch.h:118) ---- */
 /* Each writes this rank's share into the GLOBAL-size output at the bodies' original indices; with world > 1
- * the caller combines ranks (shares are disjoint). `n` is the capacity of the output in bodies (>= n_global). */
+ * the caller combines ranks (shares are disjoint). `n` is the capacity of the output in bodies (>= n_global).
+ * Barnes-Hut reorders the bodies along the Morton curve every step; the original indices travel with them. */
 int nbody_get_particles_aos(nbody_sim* sim, void* particles, int64_t n, size_t stride);
 int nbody_get_positions(nbody_sim* sim, float* posm4, int64_t n);
 int nbody_get_velocities(nbody_sim* sim, float* vel4, int64_t n);
@@ -155,7 +160,7 @@ int nbody_get_local_ids(nbody_sim* sim, int64_t* ids, int64_t cap, int64_t* n_lo
 typedef enum nbody_param {
   NBODY_PARAM_G = 0, NBODY_PARAM_EPS = 1, NBODY_PARAM_THETA = 2, NBODY_PARAM_PH_DELTA_TIME = 3,
   NBODY_PARAM_METHOD = 4, NBODY_PARAM_LEAF_SIZE = 5, NBODY_PARAM_REFERENCE_ROOT = 6, NBODY_PARAM_SHOW_OCTREE = 7,
-  NBODY_PARAM_INITIALIZED = 8 /* read-only */
+  NBODY_PARAM_INITIALIZED = 8 /* read-only */, NBODY_PARAM_MAC = 9
 } nbody_param;
 int nbody_set_param(nbody_sim* sim, int32_t which, double value);
 int nbody_get_param(nbody_sim* sim, int32_t which, double* value);
@@ -172,6 +177,14 @@ int nbody_octree_boxes(nbody_sim* sim, float* boxes7, int64_t cap, int64_t* n_bo
  * zero-copy consumers such as a renderer. Valid until the next set/clean/destroy. */
 int nbody_device_ptrs(nbody_sim* sim, void** posm4, void** vel4, void** acc4);
 
+/* Inspection of the last Barnes-Hut build (replaces walking the public Octree* ParticleOctree, OctreeSearch.h:119, through
+ * its getters h:43-48). Node k: com4[4k..] = (centre of mass xyz, total mass) as Octree::CenterOfMass / TotalMass;
+ * meta4[4k..] = (first child | first body, #children | #bodies, level + 256 * is_leaf, parent or -1); range2[2k..] = body
+ * range [begin, end) in Morton order; cell half-width (Octree::Size) = root half-width / 2^level. keys = the sorted 63-bit
+ * Morton keys (3 bits per level, 4*X + 2*Y + Z as Octree::GetOctant, h:50-56). Any output pointer may be NULL. */
+int nbody_octree_nodes(nbody_sim* sim, float* com4, int32_t* meta4, int32_t* range2, uint64_t* keys, int64_t cap_nodes,
+                       int64_t cap_keys, int64_t* n_nodes);
+
 /* ---- multi-GPU plumbing --------------------------------------------------------------------------- */
 /* 128-byte ncclUniqueId; rank 0 creates it and the launcher broadcasts it to all ranks before nbody_create. */
 int nbody_comm_unique_id(uint8_t out128[128]);
@@ -180,6 +193,10 @@ int nbody_comm_unique_id(uint8_t out128[128]);
 /* FP32 FMA-chain microbenchmark on `device`: sustained FFMA throughput in TFLOP/s (2 flops per FMA) and the
  * SM clock (MHz) implied by the in-kernel cycle counter. Used as the measured roofline denominator. */
 int nbody_measure_fp32_peak(int32_t device, double* tflops, double* sm_mhz);
+/* The Morton-key radix sort on its own (K5): host keys in, sorted keys and the STABLE permutation (idx_out[i] = input
+ * position of output i) out; the low key_bits bits are sorted. *ms (may be NULL) = best-of-3 device time of the sort. */
+int nbody_sort_pairs_u64(int32_t device, const uint64_t* keys_in, int64_t n, int32_t key_bits, uint64_t* keys_out,
+                         uint32_t* idx_out, float* ms);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ METHOD_DIRECT = 0
 METHOD_BARNES_HUT = 1
 
 PARAM_G, PARAM_EPS, PARAM_THETA, PARAM_PH_DELTA_TIME, PARAM_METHOD, PARAM_LEAF_SIZE, PARAM_REFERENCE_ROOT, \
-    PARAM_SHOW_OCTREE, PARAM_INITIALIZED = range(9)
+    PARAM_SHOW_OCTREE, PARAM_INITIALIZED, PARAM_MAC = range(10)
 
 # FParticle, OctreeSearch.h:9-18 (40 bytes)
 PARTICLE_DTYPE = np.dtype([("Mass", "<f4"), ("Position", "<f4", 3), ("Velocity", "<f4", 3), ("Acceleration", "<f4", 3)])
@@ -39,7 +39,7 @@ class _Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("method", C.c_int32), ("G", C.c_float), ("eps", C.c_float),
                 ("theta", C.c_float), ("ph_delta_time", C.c_float), ("device", C.c_int32), ("rank", C.c_int32),
                 ("world", C.c_int32), ("leaf_size", C.c_int32), ("reference_root", C.c_int32),
-                ("reserved", C.c_int32 * 5), ("nccl_unique_id", C.c_uint8 * 128), ("stream", C.c_void_p)]
+                ("mac", C.c_int32), ("reserved", C.c_int32 * 4), ("nccl_unique_id", C.c_uint8 * 128), ("stream", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -65,6 +65,7 @@ EXPORTS = [
     "nbody_synchronize", "nbody_get_particles_aos", "nbody_get_positions", "nbody_get_velocities",
     "nbody_get_accelerations", "nbody_get_local_ids", "nbody_set_param", "nbody_get_param", "nbody_energy",
     "nbody_stats_get", "nbody_octree_boxes", "nbody_device_ptrs", "nbody_comm_unique_id", "nbody_measure_fp32_peak",
+    "nbody_octree_nodes", "nbody_sort_pairs_u64",
 ]
 
 _lib = None
@@ -112,6 +113,8 @@ def load_library():
     L.nbody_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.nbody_comm_unique_id.argtypes = [vp]
     L.nbody_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.nbody_octree_nodes.argtypes = [vp, vp, vp, vp, vp, i64, i64, C.POINTER(i64)]
+    L.nbody_sort_pairs_u64.argtypes = [C.c_int32, vp, i64, C.c_int32, vp, vp, C.POINTER(C.c_float)]
     if L.nbody_abi_version() != 1:
         raise NBodyError(-1, "ABI version mismatch")
     _lib = L
@@ -128,6 +131,17 @@ def measure_fp32_peak(device: int = 0):
     t, m = C.c_double(), C.c_double()
     _check(load_library().nbody_measure_fp32_peak(device, C.byref(t), C.byref(m)))
     return t.value, m.value
+
+
+def sort_pairs_u64(keys: np.ndarray, key_bits: int = 64, device: int = 0, timed: bool = False):
+    """K5 on its own: (sorted keys, stable permutation[, device ms])."""
+    keys = np.ascontiguousarray(keys, np.uint64)
+    out_k = np.empty_like(keys)
+    out_i = np.empty(keys.shape[0], np.uint32)
+    ms = C.c_float()
+    _check(load_library().nbody_sort_pairs_u64(device, _ptr(keys), keys.shape[0], key_bits, _ptr(out_k), _ptr(out_i),
+                                               C.byref(ms) if timed else None))
+    return (out_k, out_i, ms.value) if timed else (out_k, out_i)
 
 
 def comm_unique_id() -> bytes:
@@ -151,12 +165,13 @@ class OctreeSearch:
     def __init__(self, method: int = METHOD_BARNES_HUT, G: float = 1e4, eps: float = 0.0, theta: float = 1.0,
                  PhDeltaTime: float = 0.01, device: int = 0, rank: int = 0, world: int = 1,
                  nccl_unique_id: bytes | None = None, leaf_size: int = 16, reference_root: bool = False,
-                 stream: int | None = None):
+                 mac: int = 0, stream: int | None = None):
         self._L = load_library()
         cfg = _Config()
         _check(self._L.nbody_config_default(C.byref(cfg)))
         cfg.method, cfg.G, cfg.eps, cfg.theta, cfg.ph_delta_time = method, G, eps, theta, PhDeltaTime
         cfg.device, cfg.rank, cfg.world, cfg.leaf_size, cfg.reference_root = device, rank, world, leaf_size, int(reference_root)
+        cfg.mac = mac
         if world > 1:
             if nccl_unique_id is None or len(nccl_unique_id) != 128:
                 raise NBodyError(-1, "world > 1 needs the 128-byte nccl_unique_id broadcast from rank 0")
@@ -280,6 +295,18 @@ class OctreeSearch:
         _check(self._L.nbody_octree_boxes(self._h, _ptr(out), cap, C.byref(n)))
         return out[:n.value]
 
+    def OctreeNodes(self) -> dict:
+        """The last Barnes-Hut build: per-node centre of mass + mass, (first, count, level | 256*leaf, parent), body range,
+        and the sorted Morton keys (what walking ``ParticleOctree`` through its getters gives in the reference)."""
+        n = C.c_int64()
+        _check(self._L.nbody_octree_nodes(self._h, None, None, None, None, 0, 0, C.byref(n)))
+        k, nb = n.value, self.Num()
+        com, meta = np.zeros((k, 4), np.float32), np.zeros((k, 4), np.int32)
+        rng, keys = np.zeros((k, 2), np.int32), np.zeros(nb, np.uint64)
+        _check(self._L.nbody_octree_nodes(self._h, _ptr(com), _ptr(meta), _ptr(rng), _ptr(keys), k, nb, C.byref(n)))
+        return {"com": com, "first": meta[:, 0], "count": meta[:, 1], "level": meta[:, 2] & 255,
+                "leaf": (meta[:, 2] & 256) != 0, "parent": meta[:, 3], "range": rng, "keys": keys}
+
     def DevicePtrs(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(self._L.nbody_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
@@ -319,6 +346,8 @@ class OctreeSearch:
     Eps = property(lambda s: s._getp(PARAM_EPS), lambda s, v: s._setp(PARAM_EPS, v))
     G = property(lambda s: s._getp(PARAM_G), lambda s, v: s._setp(PARAM_G, v))
     Initialized = property(lambda s: bool(s._getp(PARAM_INITIALIZED)))
+    Mac = property(lambda s: int(s._getp(PARAM_MAC)), lambda s, v: s._setp(PARAM_MAC, v))
+    LeafSize = property(lambda s: int(s._getp(PARAM_LEAF_SIZE)), lambda s, v: s._setp(PARAM_LEAF_SIZE, v))
 
     @property
     def Size(self) -> float:

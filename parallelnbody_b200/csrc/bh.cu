@@ -1,11 +1,705 @@
+// Barnes-Hut path on sm_100a: K4 Morton keys, K5 radix sort (radix_sort.cuh), K6 octree topology, K7 monopoles,
+// K8 force walk. See bh.cuh for what each replaces in the reference.
+//
+// Tree representation (all in HBM, rebuilt every step like the reference does, OctreeSearch.cpp:78-81):
+//   bodies sorted by 63-bit Morton key (21 bits per axis, X most significant as Octree::GetOctant, OctreeSearch.h:50-56),
+//   so every octree cell is a contiguous body range. Nodes form a COMPRESSED octree: a node is the smallest cell that
+//   contains its bodies (chains of one-child cells that the reference materialises, h:65-78, are skipped - they all carry
+//   the same monopole and the reference accepts the chain iff it would accept its smallest cell, so the result is the same);
+//   children of a node are contiguous in index and stored in octant order.
+//     node_com[k]  = (centre of mass xyz, total mass)                       float4
+//     node_meta[k] = (first child | first body, #children | #bodies, level | leaf flag, parent)   int4
+//     node_range[k] = (first body, one past last body)                      int2
+//   A node with <= leaf_size bodies (or at the deepest level) is a leaf. Cell half-width = root half-width / 2^level,
+//   the reference's `Size` (h:70-74).
 #include "bh.cuh"
+
+#include <algorithm>
+#include <vector>
+
+#include "direct_kernels.cuh"
+#include "radix_sort.cuh"
+
 namespace nbody {
-__global__ void iota_kernel(int32_t* ids, int n, int first) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) ids[i] = first + i; }
-void bh_reset(BHState&) {}
-void bh_free(BHState&) {}
-void bh_iota(int32_t* ids, int n, int first, cudaStream_t s) { iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, n, first); }
-int bh_build(BHState&, const BHParams&, float4**, float4**, int32_t**, int, const uint32_t*, cudaStream_t, double*) { set_error("Barnes-Hut not built yet"); return -1; }
-int bh_forces(BHState&, const BHParams&, const float4*, float4*, int, cudaStream_t, double*) { set_error("Barnes-Hut not built yet"); return -1; }
-int bh_fetch_stats(BHState&, cudaStream_t, double*) { return 0; }
-int bh_leaf_boxes(BHState&, const float4*, int, float*, int64_t, int64_t*, cudaStream_t) { set_error("Barnes-Hut not built yet"); return -1; }
+namespace {
+
+constexpr int kMaxLevel = 21;            // 3 * 21 = 63 key bits
+constexpr int kLeafFlag = 1 << 8;
+constexpr int kBodyFlag = 1 << 30;       // walk-stack entry is a body index, not a node
+constexpr int kGroupBodies = 64;         // bodies per walk group (2 per lane)
+constexpr int kWalkThreads = 256;
+constexpr int kWalkWarps = kWalkThreads / 32;
+constexpr int kStackCap = 8192;          // per-warp walk stack entries (HBM/L2 resident)
+constexpr int kListCap = 64;             // per-warp interaction ring in shared memory
+
+struct Counters {
+  int nnodes, ngroups, ticket, depth, next_group, overflow, pad0, pad1;
+  int gen_off[kMaxLevel + 4];
+  unsigned long long interactions;
+};
+
+struct Impl {
+  int64_t cap_n = 0;
+  RadixSortBuffers sort;
+  int sorted = 0;                   // which sort buffer holds the sorted keys
+  int64_t cap_nodes = 0;
+  float4* node_com = nullptr;
+  int4* node_meta = nullptr;
+  int2* node_range = nullptr;
+  uint32_t* node_ready = nullptr;
+  int2* groups = nullptr;            // walk groups: body ranges of <= kGroupBodies neighbours
+  Counters* counters = nullptr;
+  float4* root = nullptr;          // [0] = cube (centre, half-width); [1] = previous root COM (xyz) + valid flag (w)
+  int* stacks = nullptr;
+  int64_t cap_stacks = 0;
+  float* boxes = nullptr; int64_t cap_boxes = 0;
+  int n = 0;
+};
+
+Impl* impl_of(BHState& st) {
+  if (!st.impl) st.impl = new Impl();
+  return static_cast<Impl*>(st.impl);
 }
+
+template <class T>
+int realloc_dev(T** p, size_t count) {
+  if (*p) { NB_CUDA(cudaFree(*p)); *p = nullptr; }
+  NB_CUDA(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+  return 0;
+}
+
+int ensure(Impl* m, int n, cudaStream_t s) {
+  if (!m->counters) {
+    NB_TRY(realloc_dev(&m->counters, 1));
+    NB_TRY(realloc_dev(&m->root, 2));
+    NB_CUDA(cudaMemsetAsync(m->counters, 0, sizeof(Counters), s));
+    NB_CUDA(cudaMemsetAsync(m->root, 0, 2 * sizeof(float4), s));
+  }
+  if (n <= m->cap_n) return 0;
+  NB_CUDA(cudaStreamSynchronize(s));
+  const size_t c = (size_t)n + (size_t)n / 8 + 1024;
+  const size_t nblocks = ceil_div((int64_t)c, kSortTile);
+  for (int k = 0; k < 2; k++) { NB_TRY(realloc_dev(&m->sort.keys[k], c)); NB_TRY(realloc_dev(&m->sort.idx[k], c)); }
+  NB_TRY(realloc_dev(&m->sort.hist, 256 * nblocks));
+  NB_TRY(realloc_dev(&m->sort.tile_sums, ceil_div((int64_t)(256 * nblocks), kScanTile) + 1));
+  const size_t nodes = 2 * c + 8;
+  NB_TRY(realloc_dev(&m->node_com, nodes));
+  NB_TRY(realloc_dev(&m->node_meta, nodes));
+  NB_TRY(realloc_dev(&m->node_range, nodes));
+  NB_TRY(realloc_dev(&m->node_ready, nodes));
+  NB_TRY(realloc_dev(&m->groups, c));
+  m->cap_nodes = (int64_t)nodes;
+  m->cap_n = (int64_t)c;
+  return 0;
+}
+
+// ---- K4: root cube + Morton keys -----------------------------------------------------------------------------
+// box = cube_size_kernel output. reference_root: centre = previous root COM (0 on the first build), half-width =
+// max |coordinate| (OctreeSearch.cpp:47-56,77-79) - such a cube need not contain every body, exactly as in the
+// reference, where outliers are still routed by the octant comparisons; here their quantised coordinates clamp.
+// Otherwise: the tight bounding cube.
+__global__ void root_cube_kernel(const uint32_t* __restrict__ box, const int reference_root, float4* __restrict__ root) {
+  float cx, cy, cz, half;
+  if (reference_root) {
+    const float4 prev = root[1];
+    cx = prev.x; cy = prev.y; cz = prev.z;
+    half = __uint_as_float(box[0]);
+  } else {
+    const float lx = ordered_to_float(box[1]), ly = ordered_to_float(box[2]), lz = ordered_to_float(box[3]);
+    const float hx = ordered_to_float(box[4]), hy = ordered_to_float(box[5]), hz = ordered_to_float(box[6]);
+    cx = 0.5f * (lx + hx); cy = 0.5f * (ly + hy); cz = 0.5f * (lz + hz);
+    half = 0.5f * fmaxf(fmaxf(hx - lx, hy - ly), hz - lz);
+    half = half * 1.0001f + 1e-30f;
+  }
+  if (!(half > 0.f) || !isfinite(half)) half = 1.f;
+  root[0] = make_float4(cx, cy, cz, half);
+}
+
+__device__ __forceinline__ uint64_t expand21(uint32_t v) {
+  uint64_t x = v & 0x1fffffu;
+  x = (x | x << 32) & 0x001f00000000ffffull;
+  x = (x | x << 16) & 0x001f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+__device__ __forceinline__ uint32_t compact21(uint64_t x) {
+  x &= 0x1249249249249249ull;
+  x = (x | x >> 2) & 0x10c30c30c30c30c3ull;
+  x = (x | x >> 4) & 0x100f00f00f00f00full;
+  x = (x | x >> 8) & 0x001f0000ff0000ffull;
+  x = (x | x >> 16) & 0x001f00000000ffffull;
+  x = (x | x >> 32) & 0x1fffffull;
+  return (uint32_t)x;
+}
+__device__ __forceinline__ uint32_t quantize(float x, float lo, float scale) {
+  const float f = floorf((x - lo) * scale);
+  return (uint32_t)fminf(fmaxf(f, 0.f), 2097151.f);
+}
+
+__global__ void __launch_bounds__(256)
+morton_kernel(const float4* __restrict__ posm, const int n, const float4* __restrict__ root, uint64_t* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 c = root[0];
+  const float scale = 1048576.f / c.w;  // 2^21 cells across the full width 2 * half
+  const float4 p = ld_stream(posm + i);
+  const uint32_t qx = quantize(p.x, c.x - c.w, scale), qy = quantize(p.y, c.y - c.w, scale), qz = quantize(p.z, c.z - c.w, scale);
+  keys[i] = expand21(qx) << 2 | expand21(qy) << 1 | expand21(qz);   // octant digit = 4*X + 2*Y + Z (OctreeSearch.h:50-56)
+}
+
+__global__ void __launch_bounds__(256)
+gather_bodies_kernel(const uint32_t* __restrict__ order, const int n, const float4* __restrict__ posm_in,
+                     const float4* __restrict__ vel_in, const int32_t* __restrict__ ids_in, float4* __restrict__ posm_out,
+                     float4* __restrict__ vel_out, int32_t* __restrict__ ids_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t j = order[i];
+  st_stream(posm_out + i, posm_in[j]);
+  st_stream(vel_out + i, vel_in[j]);
+  ids_out[i] = ids_in[j];
+}
+
+// ---- K6: octree topology ------------------------------------------------------------------------------------
+// Number of leading 3-bit digits two keys share = level of the smallest cell containing both.
+__device__ __forceinline__ int common_levels(uint64_t a, uint64_t b) {
+  const uint64_t x = a ^ b;
+  if (x == 0) return kMaxLevel;
+  return (__clzll((long long)x) - 1) / 3;
+}
+
+__global__ void tree_init_kernel(const uint64_t* __restrict__ keys, const int n, int2* __restrict__ range,
+                                 int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
+                                 Counters* __restrict__ c) {
+  const int lvl = n > 1 ? common_levels(keys[0], keys[n - 1]) : kMaxLevel;
+  range[0] = make_int2(0, n);
+  meta[0] = make_int4(0, 0, lvl, -1);
+  ready[0] = 0;
+  c->nnodes = 1; c->ngroups = 0; c->ticket = 0; c->depth = 0; c->next_group = 0; c->overflow = 0;
+  for (int k = 0; k < kMaxLevel + 4; k++) c->gen_off[k] = 1;
+  c->gen_off[0] = 0;
+  c->interactions = 0;
+  if (n <= kGroupBodies) { groups[0] = make_int2(0, n); c->ngroups = 1; }
+}
+
+// One generation of the top-down split: every node created by the previous generation either becomes a leaf or is cut
+// at its level's octant digit into its non-empty children (8 lanes per node, one octant boundary each, found by
+// binary search in the sorted keys). Equivalent of the recursive re-insertion in Octree::Add (OctreeSearch.h:65-78).
+__global__ void __launch_bounds__(256)
+tree_split_kernel(const int gen, const uint64_t* __restrict__ keys, const int leaf_size, int2* __restrict__ range,
+                  int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
+                  Counters* __restrict__ c) {
+  const int gb = c->gen_off[gen], ge = c->gen_off[gen + 1];
+  const int lane = threadIdx.x & 31, sub = lane & 7, gshift = lane & ~7;
+  const unsigned gmask = 0xffu << gshift;
+  const int stride = gridDim.x * blockDim.x / 8;
+  int maxlvl = 0;
+  for (int node = gb + (blockIdx.x * blockDim.x + threadIdx.x) / 8; node < ge; node += stride) {
+    const int2 r = range[node];
+    const int4 m = meta[node];
+    const int cnt = r.y - r.x, level = m.z;
+    if (cnt <= leaf_size || level >= kMaxLevel) {
+      if (sub == 0) {
+        meta[node] = make_int4(r.x, cnt, level | kLeafFlag, m.w);
+        // > kGroupBodies bodies in one deepest-level cell (coincident to 2^-21 of the cube): walk them in chunks
+        if (cnt > kGroupBodies) {
+          const int chunks = (cnt + kGroupBodies - 1) / kGroupBodies;
+          const int g0 = atomicAdd(&c->ngroups, chunks);
+          for (int k = 0; k < chunks; k++) groups[g0 + k] = make_int2(r.x + k * kGroupBodies, min(r.y, r.x + (k + 1) * kGroupBodies));
+        }
+      }
+      maxlvl = max(maxlvl, m.w >= 0 ? (meta[m.w].z & 255) + 1 : 0);   // depth of the leaf's cell in the reference's tree
+      continue;
+    }
+    const int shift = 3 * (kMaxLevel - 1 - level);
+    int lo = r.x, hi = r.y;
+    while (lo < hi) {  // first body whose digit at this level is >= sub
+      const int mid = (lo + hi) >> 1;
+      if ((int)((keys[mid] >> shift) & 7ull) < sub) lo = mid + 1; else hi = mid;
+    }
+    const int start = lo;
+    int next = __shfl_down_sync(gmask, start, 1, 8);
+    if (sub == 7) next = r.y;
+    const int cc = next - start;
+    const unsigned nonempty = (__ballot_sync(gmask, cc > 0) >> gshift) & 0xffu;
+    const int nchild = __popc(nonempty), slot = __popc(nonempty & ((1u << sub) - 1u));
+    int base = 0;
+    if (sub == 0) base = atomicAdd(&c->nnodes, nchild);
+    base = __shfl_sync(gmask, base, gshift);
+    if (cc > 0) {
+      const int child = base + slot;
+      range[child] = make_int2(start, next);
+      meta[child] = make_int4(0, 0, cc > 1 ? common_levels(keys[start], keys[next - 1]) : kMaxLevel, node);
+      ready[child] = 0;
+      if (cc <= kGroupBodies && cnt > kGroupBodies) groups[atomicAdd(&c->ngroups, 1)] = make_int2(start, next);
+    }
+    if (sub == 0) meta[node] = make_int4(base, nchild, level, m.w);
+  }
+  if (maxlvl) atomicMax(&c->depth, maxlvl);
+  // the last CTA to finish publishes where the next generation ends
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&c->ticket, 1);
+    if (t == (int)gridDim.x - 1) {
+      c->gen_off[gen + 2] = *((volatile int*)&c->nnodes);
+      c->ticket = 0;
+    }
+  }
+}
+
+// ---- K7: monopoles (Octree::ComputeMass, OctreeSearch.h:83-97) ---------------------------------------------------
+// Leaves sum their bodies; the last child to arrive at a parent sums the parent's children in octant order:
+//   TotalMass += Mc;  CenterOfMass += COMc * Mc;  CenterOfMass *= 1 / TotalMass   (fp32, as the reference; M == 0 keeps
+// a position inside the cell, h:95), with the first-order sums taken about the first child.
+__global__ void __launch_bounds__(256)
+monopole_kernel(const float4* __restrict__ posm, const int2* __restrict__ range, const int4* __restrict__ meta,
+                uint32_t* __restrict__ ready, float4* __restrict__ com, const Counters* __restrict__ c,
+                float4* __restrict__ root) {
+  const int nn = c->nnodes;
+  for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < nn; node += gridDim.x * blockDim.x) {
+    int4 m = meta[node];
+    if (!(m.z & kLeafFlag)) continue;
+    // sums are taken about the first member (mathematically the same COM; exact when the members coincide, so a
+    // body never sees its own cell's monopole at a rounding-error distance)
+    const float4 p0 = posm[m.x];
+    float M = 0.f, x = 0.f, y = 0.f, z = 0.f;
+    for (int b = m.x; b < m.x + m.y; b++) {
+      const float4 p = posm[b];
+      M += p.w; x += (p.x - p0.x) * p.w; y += (p.y - p0.y) * p.w; z += (p.z - p0.z) * p.w;
+    }
+    if (M != 0.f) { const float rv = 1.f / M; x = p0.x + x * rv; y = p0.y + y * rv; z = p0.z + z * rv; }
+    else { x = p0.x; y = p0.y; z = p0.z; }
+    __stcg(com + node, make_float4(x, y, z, M));
+    while (true) {
+      const int parent = m.w;
+      if (parent < 0) { root[1] = make_float4(x, y, z, 1.f); break; }   // next reference-mode root centre (OctreeSearch.cpp:77)
+      __threadfence();
+      m = meta[parent];
+      if (atomicAdd(ready + parent, 1u) != (uint32_t)(m.y - 1)) break;
+      __threadfence();
+      const float4 q0 = __ldcg(com + m.x);
+      M = 0.f; x = 0.f; y = 0.f; z = 0.f;
+      for (int k = 0; k < m.y; k++) {
+        const float4 q = __ldcg(com + m.x + k);
+        M += q.w; x += (q.x - q0.x) * q.w; y += (q.y - q0.y) * q.w; z += (q.z - q0.z) * q.w;
+      }
+      if (M != 0.f) { const float rv = 1.f / M; x = q0.x + x * rv; y = q0.y + y * rv; z = q0.z + z * rv; }
+      else { x = q0.x; y = q0.y; z = q0.z; }
+      __stcg(com + parent, make_float4(x, y, z, M));
+    }
+  }
+}
+
+// ---- K8a: warp-coherent group walk ----------------------------------------------------------------------------
+// One warp per group of <= 64 Morton-neighbouring bodies (2 per lane, in registers). The warp pops up to 32 stack
+// entries per round, one per lane; each lane tests its cell against the GROUP's bounding box:
+//     accept  <=>  half-width / dmin < theta,  dmin = distance(box, cell COM)          (cf. Size / d < Theta, h:103)
+// dmin <= every member's own d, so an accepted cell is one the reference would accept for each member. Accepted cells
+// and the bodies of opened leaves are appended to a 64-entry ring in shared memory; whenever 32 are pending, all lanes
+// evaluate them against their bodies with the direct-sum interaction (FP32-pipe bound, no divergence). Opened cells
+// push their children. The stack lives in a per-warp slab of global memory (L2 resident, coalesced).
+template <bool EPS0>
+__device__ __forceinline__ void eval_list(const float4* __restrict__ ring, const int head,
+                                          const float (&px)[2], const float (&py)[2], const float (&pz)[2], const float eps2,
+                                          float (&ax)[2], float (&ay)[2], float (&az)[2]) {
+#pragma unroll 8
+  for (int j = 0; j < 32; j++) {
+    const float4 s = ring[(head + j) & (kListCap - 1)];
+    interact<EPS0>(s, px[0], py[0], pz[0], eps2, ax[0], ay[0], az[0]);
+    interact<EPS0>(s, px[1], py[1], pz[1], eps2, ax[1], ay[1], az[1]);
+  }
+}
+
+template <bool EPS0>
+__global__ void __launch_bounds__(kWalkThreads)
+bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com, const int4* __restrict__ node_meta,
+                     const int2* __restrict__ groups, Counters* __restrict__ c,
+                     const float4* __restrict__ root, const float theta2, const float eps2, const float G, const int t0,
+                     const int t1, int* __restrict__ stacks, float4* __restrict__ acc) {
+  __shared__ float4 ring_all[kWalkWarps][kListCap];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float4* ring = ring_all[w];
+  int* stack = stacks + (size_t)(blockIdx.x * kWalkWarps + w) * kStackCap;
+  const int ngroups = c->ngroups;
+  const float root_half = root[0].w;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned long long inter = 0;
+  while (true) {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(&c->next_group, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= ngroups) break;
+    const int2 r = groups[g];
+    const int ntarget = min(r.y, t1) - max(r.x, t0);
+    if (ntarget <= 0) continue;
+    float px[2], py[2], pz[2], ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f}, az[2] = {0.f, 0.f};
+    float lox = 3.4e38f, loy = 3.4e38f, loz = 3.4e38f, hix = -3.4e38f, hiy = -3.4e38f, hiz = -3.4e38f;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int i = r.x + lane + 32 * k;
+      const float4 p = posm[i < r.y ? i : r.x];
+      px[k] = p.x; py[k] = p.y; pz[k] = p.z;
+      lox = fminf(lox, p.x); loy = fminf(loy, p.y); loz = fminf(loz, p.z);
+      hix = fmaxf(hix, p.x); hiy = fmaxf(hiy, p.y); hiz = fmaxf(hiz, p.z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+      loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+      loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+    }
+    const float gcx = 0.5f * (lox + hix), gcy = 0.5f * (loy + hiy), gcz = 0.5f * (loz + hiz);
+    const float ghx = 0.5f * (hix - lox), ghy = 0.5f * (hiy - loy), ghz = 0.5f * (hiz - loz);
+
+    int top = 1, head = 0, pending = 0;
+    if (lane == 0) stack[0] = 0;
+    __syncwarp();
+    unsigned long long entries = 0;
+    while (top > 0) {
+      const int nb = min(32, top);
+      top -= nb;
+      const int e = lane < nb ? stack[top + lane] : -1;
+      float4 item = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool has_item = false;
+      int push_first = 0, push_n = 0, push_flag = 0;
+      if (e >= 0) {
+        if (e & kBodyFlag) {
+          item = posm[e & ~kBodyFlag];
+          has_item = true;
+        } else {
+          const float4 cm = node_com[e];
+          const int4 m = node_meta[e];
+          const bool leaf = (m.z & kLeafFlag) != 0;
+          const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);   // half-width / 2^level
+          const float dx = fmaxf(fabsf(cm.x - gcx) - ghx, 0.f), dy = fmaxf(fabsf(cm.y - gcy) - ghy, 0.f),
+                      dz = fmaxf(fabsf(cm.z - gcz) - ghz, 0.f);
+          const float dmin2 = dx * dx + dy * dy + dz * dz;
+          if (size * size < theta2 * dmin2 || (leaf && m.y == 1)) { item = cm; has_item = true; }
+          else { push_first = m.x; push_n = m.y; push_flag = leaf ? kBodyFlag : 0; }
+        }
+      }
+      // children / leaf bodies of the opened cells go on the stack
+      int incl = push_n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (top + total > kStackCap) { if (lane == 0) atomicExch(&c->overflow, 1); top = 0; pending = 0; break; }
+      int* dst = stack + top + incl - push_n;
+      for (int k = 0; k < push_n; k++) dst[k] = (push_first + k) | push_flag;
+      top += total;
+      // accepted cells / bodies join the pending interaction ring
+      const unsigned mask = __ballot_sync(0xffffffffu, has_item);
+      if (has_item) ring[(head + pending + __popc(mask & lt)) & (kListCap - 1)] = item;
+      pending += __popc(mask);
+      __syncwarp();
+      if (pending >= 32) {
+        eval_list<EPS0>(ring, head, px, py, pz, eps2, ax, ay, az);
+        head = (head + 32) & (kListCap - 1);
+        pending -= 32;
+        entries += 32;
+        __syncwarp();
+      }
+    }
+    if (pending > 0) {  // tail: pad the ring with massless entries so the evaluation stays branch-free
+      if (lane >= pending) ring[(head + lane) & (kListCap - 1)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      eval_list<EPS0>(ring, head, px, py, pz, eps2, ax, ay, az);
+      entries += pending;
+      __syncwarp();
+    }
+    inter += entries * (unsigned long long)ntarget;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int i = r.x + lane + 32 * k;
+      if (i < r.y && i >= t0 && i < t1) acc[i] = make_float4(G * ax[k], G * ay[k], G * az[k], 0.f);
+    }
+  }
+  if (lane == 0 && inter) atomicAdd(&c->interactions, inter);
+}
+
+// ---- K8b: per-body walk with the reference's exact rule and order (parity mode) ---------------------------------
+// Octree::ComputeForces (OctreeSearch.h:99-108): d = |COM - x| (fp32 sqrtf); d == 0 -> skip; accept when Size / d < Theta or
+// one-body leaf: a += (float)(G * M / d^3) * (COM - x), scalar in double; else the children in octant order.
+__device__ __forceinline__ void ref_pair(const float4 s, const float4 p, const float G, const float eps2, float& ax, float& ay,
+                                         float& az, int& count) {
+  const float dx = __fsub_rn(p.x, s.x), dy = __fsub_rn(p.y, s.y), dz = __fsub_rn(p.z, s.z);
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  float d = sqrtf(d2);
+  if (d == 0.f) return;
+  if (eps2 > 0.f) d = sqrtf(__fadd_rn(d2, eps2));
+  const double dd = (double)d;
+  const float sc = (float)((double)G * (double)s.w / (dd * dd * dd));
+  ax = __fadd_rn(ax, __fmul_rn(__fsub_rn(s.x, p.x), sc));
+  ay = __fadd_rn(ay, __fmul_rn(__fsub_rn(s.y, p.y), sc));
+  az = __fadd_rn(az, __fmul_rn(__fsub_rn(s.z, p.z), sc));
+  count++;
+}
+
+__global__ void __launch_bounds__(128)
+bh_walk_body_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com, const int4* __restrict__ node_meta,
+                    Counters* __restrict__ c, const float4* __restrict__ root, const float theta, const float eps2,
+                    const float G, const int t0, const int t1, float4* __restrict__ acc) {
+  const int i = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+  int count = 0;
+  if (i < t1) {
+    const float4 p = posm[i];
+    const float root_half = root[0].w;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    int stack[kMaxLevel * 7 + 16];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+      const int e = stack[--sp];
+      const float4 cm = node_com[e];
+      const int4 m = node_meta[e];
+      const float dx = __fsub_rn(p.x, cm.x), dy = __fsub_rn(p.y, cm.y), dz = __fsub_rn(p.z, cm.z);
+      const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      if (d == 0.f) continue;                                                 // h:102
+      const bool leaf = (m.z & kLeafFlag) != 0;
+      const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);
+      if (__fdiv_rn(size, d) < theta || (leaf && m.y == 1)) {                 // h:103
+        ref_pair(cm, p, G, eps2, ax, ay, az, count);                          // h:104
+      } else if (leaf) {
+        for (int b = m.x; b < m.x + m.y; b++) ref_pair(posm[b], p, G, eps2, ax, ay, az, count);
+      } else {
+        for (int k = m.y - 1; k >= 0; k--) stack[sp++] = m.x + k;             // popped in octant order (h:105-107)
+      }
+    }
+    acc[i] = make_float4(ax, ay, az, 0.f);
+  }
+  // interaction count: warp-reduce then one atomic per warp
+  unsigned long long v = (unsigned long long)count;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(&c->interactions, v);
+}
+
+// ---- read-back of what DrawOctreeBoxes draws (OctreeSearch.cpp:36-45): one box per occupied leaf ---------------------
+__global__ void __launch_bounds__(256)
+leaf_boxes_kernel(const uint64_t* __restrict__ keys, const int4* __restrict__ meta, const Counters* __restrict__ c,
+                  const float4* __restrict__ root, float* __restrict__ boxes7, const int cap, int* __restrict__ nout) {
+  const int nn = c->nnodes;
+  const float4 rc = root[0];
+  for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < nn; node += gridDim.x * blockDim.x) {
+    const int4 m = meta[node];
+    if (!(m.z & kLeafFlag) || m.y <= 0) continue;
+    // the cell this leaf hangs in: one level below its parent (the reference's leaf cell), the root itself if alone
+    const int lvl = m.w < 0 ? 0 : min((meta[m.w].z & 255) + 1, kMaxLevel);
+    const uint64_t key = keys[m.x];
+    const int drop = kMaxLevel - lvl;
+    const uint32_t qx = compact21(key >> 2) >> drop, qy = compact21(key >> 1) >> drop, qz = compact21(key) >> drop;
+    const float half = rc.w * __int_as_float((127 - lvl) << 23);
+    const int slot = atomicAdd(nout, 1);
+    if (slot < cap) {
+      float* o = boxes7 + (size_t)slot * 7;
+      o[0] = rc.x - rc.w + (2.f * (float)qx + 1.f) * half;
+      o[1] = rc.y - rc.w + (2.f * (float)qy + 1.f) * half;
+      o[2] = rc.z - rc.w + (2.f * (float)qz + 1.f) * half;
+      o[3] = half; o[4] = half; o[5] = half;
+      o[6] = (float)m.y;
+    }
+  }
+}
+
+__global__ void iota_kernel(int32_t* ids, int n, int first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = first + i;
+}
+
+int walk_grid(bool eps0) {
+  int per_sm = 0;
+  if (eps0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<true>, kWalkThreads, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<false>, kWalkThreads, 0);
+  per_sm = std::max(1, std::min(per_sm, 8));
+  return kNumSMsB200 * per_sm;
+}
+
+}  // namespace
+
+void bh_reset(BHState& st, cudaStream_t s) {
+  st.n_nodes_host = st.depth_host = st.n_groups_host = 0;
+  st.root_mass_host = 0;
+  for (int k = 0; k < 3; k++) st.root_com_host[k] = 0;
+  if (st.impl) {
+    Impl* m = static_cast<Impl*>(st.impl);
+    if (m->root) cudaMemsetAsync(m->root, 0, 2 * sizeof(float4), s);
+    m->n = 0;
+  }
+}
+
+void bh_free(BHState& st) {
+  if (!st.impl) return;
+  Impl* m = static_cast<Impl*>(st.impl);
+  for (int k = 0; k < 2; k++) { cudaFree(m->sort.keys[k]); cudaFree(m->sort.idx[k]); }
+  cudaFree(m->sort.hist); cudaFree(m->sort.tile_sums);
+  cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->groups);
+  cudaFree(m->counters); cudaFree(m->root); cudaFree(m->stacks); cudaFree(m->boxes);
+  delete m;
+  st.impl = nullptr;
+}
+
+void bh_iota(int32_t* ids, int n, int first, cudaStream_t s) {
+  if (n > 0) iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, n, first);
+}
+
+int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
+             float4* posm, float4* vel, int32_t* ids, int n, const uint32_t* box, cudaStream_t s, double* launches) {
+  if (n <= 0) { set_error("Barnes-Hut: no bodies"); return -1; }
+  if (n > (1 << 28)) { set_error("Barnes-Hut: at most 2^28 bodies per GPU"); return -1; }
+  Impl* m = impl_of(st);
+  NB_TRY(ensure(m, n, s));
+  m->n = n;
+  const unsigned nb = (unsigned)ceil_div(n, 256);
+  root_cube_kernel<<<1, 1, 0, s>>>(box, p.reference_root ? 1 : 0, m->root);
+  morton_kernel<<<nb, 256, 0, s>>>(posm_in, n, m->root, m->sort.keys[0]);
+  *launches += 2;
+  m->sorted = radix_sort_pairs(m->sort, n, 3 * kMaxLevel, s, launches);
+  gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[m->sorted], n, posm_in, vel_in, ids_in, posm, vel, ids);
+  const uint64_t* keys = m->sort.keys[m->sorted];
+  tree_init_kernel<<<1, 1, 0, s>>>(keys, n, m->node_range, m->node_meta, m->node_ready, m->groups, m->counters);
+  *launches += 2;
+  const int grid = kNumSMsB200 * 4;
+  for (int gen = 0; gen <= kMaxLevel; gen++)
+    tree_split_kernel<<<grid, 256, 0, s>>>(gen, keys, std::max(1, p.leaf_size), m->node_range, m->node_meta, m->node_ready,
+                                           m->groups, m->counters);
+  monopole_kernel<<<grid, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
+  *launches += kMaxLevel + 2;
+  NB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bh_forces(BHState& st, const BHParams& p, const float4* posm, float4* acc, int n, int t0, int t1, cudaStream_t s,
+              double* launches) {
+  Impl* m = impl_of(st);
+  if (m->n != n || !m->counters) { set_error("Barnes-Hut: forces requested without a tree for these bodies"); return -5; }
+  if (t1 <= t0) return 0;
+  const bool eps0 = !(p.eps2 > 0.f);
+  if (p.mac == kMacBody) {
+    bh_walk_body_kernel<<<(unsigned)ceil_div(t1 - t0, 128), 128, 0, s>>>(posm, m->node_com, m->node_meta, m->counters, m->root,
+                                                                          p.theta, p.eps2, p.G, t0, t1, acc);
+  } else {
+    const int grid = walk_grid(eps0);
+    const int64_t need = (int64_t)grid * kWalkWarps * kStackCap;
+    if (need > m->cap_stacks) {
+      NB_CUDA(cudaStreamSynchronize(s));
+      NB_TRY(realloc_dev(&m->stacks, (size_t)need));
+      m->cap_stacks = need;
+    }
+    const float theta2 = p.theta * p.theta;
+    if (eps0)
+      bh_walk_group_kernel<true><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, m->groups,
+                                                               m->counters, m->root, theta2, p.eps2, p.G, t0, t1, m->stacks, acc);
+    else
+      bh_walk_group_kernel<false><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, m->groups,
+                                                                m->counters, m->root, theta2, p.eps2, p.G, t0, t1, m->stacks, acc);
+  }
+  *launches += 1;
+  NB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bh_fetch_stats(BHState& st, cudaStream_t s, double* interactions) {
+  if (!st.impl) return 0;
+  Impl* m = static_cast<Impl*>(st.impl);
+  if (!m->counters) return 0;
+  Counters h;
+  float4 root[2];
+  float4 com0 = make_float4(0, 0, 0, 0);
+  NB_CUDA(cudaMemcpyAsync(&h, m->counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+  NB_CUDA(cudaMemcpyAsync(root, m->root, sizeof(root), cudaMemcpyDeviceToHost, s));
+  if (m->node_com) NB_CUDA(cudaMemcpyAsync(&com0, m->node_com, sizeof(com0), cudaMemcpyDeviceToHost, s));
+  NB_CUDA(cudaStreamSynchronize(s));
+  st.n_nodes_host = h.nnodes; st.depth_host = h.depth; st.n_groups_host = h.ngroups;
+  st.root_com_host[0] = com0.x; st.root_com_host[1] = com0.y; st.root_com_host[2] = com0.z;
+  st.root_mass_host = com0.w;
+  st.root_cube_host[0] = root[0].x; st.root_cube_host[1] = root[0].y; st.root_cube_host[2] = root[0].z; st.root_cube_host[3] = root[0].w;
+  if (interactions) *interactions = (double)h.interactions;
+  if (h.overflow) { set_error("Barnes-Hut: a walk stack overflowed (leaf_size too large for kStackCap)"); return -5; }
+  if ((int64_t)h.nnodes > m->cap_nodes) { set_error("Barnes-Hut: node pool exhausted"); return -5; }
+  return 0;
+}
+
+int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t cap, int64_t* n_boxes, cudaStream_t s) {
+  (void)posm;
+  Impl* m = impl_of(st);
+  if (m->n != n || n <= 0 || !m->counters) { set_error("Barnes-Hut: no tree has been built (call CreateOctree / Tick first)"); return -5; }
+  const int64_t want = std::min<int64_t>(std::max<int64_t>(cap, 1), n);
+  if (want * 7 + 1 > m->cap_boxes) {
+    NB_CUDA(cudaStreamSynchronize(s));
+    NB_TRY(realloc_dev(&m->boxes, (size_t)(want * 7 + 1)));
+    m->cap_boxes = want * 7 + 1;
+  }
+  int* d_count = reinterpret_cast<int*>(m->boxes + want * 7);
+  NB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
+  leaf_boxes_kernel<<<kNumSMsB200 * 4, 256, 0, s>>>(m->sort.keys[m->sorted], m->node_meta, m->counters, m->root, m->boxes,
+                                                     (int)want, d_count);
+  NB_CUDA(cudaGetLastError());
+  int count = 0;
+  NB_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+  NB_CUDA(cudaStreamSynchronize(s));
+  const int64_t k = std::min<int64_t>(count, want);
+  if (boxes7 && k > 0) NB_CUDA(cudaMemcpy(boxes7, m->boxes, (size_t)k * 7 * sizeof(float), cudaMemcpyDeviceToHost));
+  *n_boxes = count;
+  return 0;
+}
+
+// ---- inspection (tests / tools): tree read-back and the stand-alone sort --------------------------------------------
+int bh_read_tree(BHState& st, float* com4, int32_t* meta4, int32_t* range2, uint64_t* keys, int64_t cap_nodes, int64_t cap_keys,
+                 int64_t* n_nodes, cudaStream_t s) {
+  Impl* m = impl_of(st);
+  if (m->n <= 0 || !m->counters) { set_error("Barnes-Hut: no tree has been built (call CreateOctree / Tick first)"); return -5; }
+  Counters h;
+  NB_CUDA(cudaMemcpyAsync(&h, m->counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+  NB_CUDA(cudaStreamSynchronize(s));
+  if (n_nodes) *n_nodes = h.nnodes;
+  const size_t k = (size_t)std::min<int64_t>(h.nnodes, cap_nodes);
+  if (com4 && k) NB_CUDA(cudaMemcpyAsync(com4, m->node_com, k * sizeof(float4), cudaMemcpyDeviceToHost, s));
+  if (meta4 && k) NB_CUDA(cudaMemcpyAsync(meta4, m->node_meta, k * sizeof(int4), cudaMemcpyDeviceToHost, s));
+  if (range2 && k) NB_CUDA(cudaMemcpyAsync(range2, m->node_range, k * sizeof(int2), cudaMemcpyDeviceToHost, s));
+  const size_t kk = (size_t)std::min<int64_t>(m->n, cap_keys);
+  if (keys && kk) NB_CUDA(cudaMemcpyAsync(keys, m->sort.keys[m->sorted], kk * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  NB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sort_pairs_host(const uint64_t* keys_in, int64_t n, int key_bits, uint64_t* keys_out, uint32_t* idx_out, float* ms) {
+  if (n <= 0 || n > (1ll << 30)) { set_error("sort: n out of range"); return -1; }
+  RadixSortBuffers b;
+  const size_t nblocks = ceil_div(n, kSortTile);
+  int rc = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto body = [&]() -> int {
+    for (int k = 0; k < 2; k++) { NB_TRY(realloc_dev(&b.keys[k], (size_t)n)); NB_TRY(realloc_dev(&b.idx[k], (size_t)n)); }
+    NB_TRY(realloc_dev(&b.hist, 256 * nblocks));
+    NB_TRY(realloc_dev(&b.tile_sums, ceil_div((int64_t)(256 * nblocks), kScanTile) + 1));
+    NB_CUDA(cudaEventCreate(&e0));
+    NB_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    int out = 0;
+    for (int rep = 0; rep < (ms ? 3 : 1); rep++) {
+      NB_CUDA(cudaMemcpy(b.keys[0], keys_in, (size_t)n * 8, cudaMemcpyHostToDevice));
+      NB_CUDA(cudaEventRecord(e0, 0));
+      out = radix_sort_pairs(b, (int)n, key_bits, 0, nullptr);
+      NB_CUDA(cudaEventRecord(e1, 0));
+      NB_CUDA(cudaEventSynchronize(e1));
+      float t;
+      NB_CUDA(cudaEventElapsedTime(&t, e0, e1));
+      best = std::min(best, t);
+    }
+    NB_CUDA(cudaGetLastError());
+    if (ms) *ms = best;
+    if (keys_out) NB_CUDA(cudaMemcpy(keys_out, b.keys[out], (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (idx_out) NB_CUDA(cudaMemcpy(idx_out, b.idx[out], (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  rc = body();
+  for (int k = 0; k < 2; k++) { cudaFree(b.keys[k]); cudaFree(b.idx[k]); }
+  cudaFree(b.hist); cudaFree(b.tile_sums);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  return rc;
+}
+
+}  // namespace nbody

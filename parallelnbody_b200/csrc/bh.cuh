@@ -1,31 +1,56 @@
-// Barnes-Hut path (K4-K8) - interface used by nbody_sim.cu. (Implementation lands in bh.cu.)
+// Barnes-Hut path (K4-K8) - interface used by nbody_sim.cu; implementation in bh.cu.
+//
+// Replaces class Octree of the reference (/root/reference/Source/NBody/OctreeSearch.h:21-109): Add (h:60-81) becomes
+// Morton keys + radix sort + a top-down split of sorted key ranges; ComputeMass (h:83-97) a bottom-up monopole pass;
+// ComputeForces (h:99-108) a warp-coherent stack walk (production) or a per-body depth-first walk with the reference's
+// exact acceptance rule and visiting order (parity mode).
 #pragma once
 #include "common.cuh"
 
 namespace nbody {
 
+enum BHMac : int {
+  kMacGroup = 0,  // one warp walks for a group of <= 64 neighbouring bodies; a cell is accepted when
+                  // half-width / (distance from the group's bounding box to the cell's centre of mass) < theta.
+                  // Never accepts a cell the reference's per-body test (OctreeSearch.h:103) would open.
+  kMacBody = 1    // per body, exactly OctreeSearch.h:100-107: skip d == 0, accept when Size / d < Theta or one-body leaf,
+                  // children visited in octant order
+};
+
 struct BHParams {
   float G = 1e4f, eps2 = 0.f, theta = 1.f;
   int leaf_size = 16;
   bool reference_root = false;
+  int mac = kMacGroup;
 };
 
 struct BHState {
-  int n_nodes_host = 0, depth_host = 0;
+  int n_nodes_host = 0, depth_host = 0, n_groups_host = 0;
   float root_com_host[3] = {0, 0, 0};
   float root_mass_host = 0;
+  float root_cube_host[4] = {0, 0, 0, 0};  // centre xyz, half-width
   void* impl = nullptr;
 };
 
-void bh_reset(BHState& st);
+// Forget the previous tree (the next reference-mode root is centred on the origin, OctreeSearch.cpp:77).
+void bh_reset(BHState& st, cudaStream_t s);
 void bh_free(BHState& st);
 void bh_iota(int32_t* ids, int n, int first, cudaStream_t s);
-// Sorts the bodies along the Morton curve (posm/vel/ids are permuted; the pointers may be swapped with internal
-// double buffers), builds the tree and its monopoles. box = launch_cube_size output.
-int bh_build(BHState& st, const BHParams& p, float4** posm, float4** vel, int32_t** ids, int n, const uint32_t* box,
-             cudaStream_t s, double* launches);
-int bh_forces(BHState& st, const BHParams& p, const float4* posm, float4* acc, int n, cudaStream_t s, double* launches);
+// Sorts the n bodies along the Morton curve (*_in -> posm / vel / ids, which must not alias the inputs), builds the
+// tree over the sorted bodies and its monopoles. box = cube_size_kernel output (absmax, min xyz, max xyz).
+int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
+             float4* posm, float4* vel, int32_t* ids, int n, const uint32_t* box, cudaStream_t s, double* launches);
+// Accelerations (G applied) of the sorted bodies [t0, t1) -> acc[t0 .. t1).
+int bh_forces(BHState& st, const BHParams& p, const float4* posm, float4* acc, int n, int t0, int t1, cudaStream_t s,
+              double* launches);
+// Synchronises; fills the *_host fields and the interaction count of the last bh_forces.
 int bh_fetch_stats(BHState& st, cudaStream_t s, double* interactions);
 int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t cap, int64_t* n_boxes, cudaStream_t s);
+
+// Inspection: copies the first cap_nodes nodes (com float4, meta int4, range int2) and the sorted Morton keys to the host.
+int bh_read_tree(BHState& st, float* com4, int32_t* meta4, int32_t* range2, uint64_t* keys, int64_t cap_nodes, int64_t cap_keys,
+                 int64_t* n_nodes, cudaStream_t s);
+// Stand-alone K5: host keys in, sorted keys + the stable permutation out; *ms (optional) = best-of-3 device time.
+int sort_pairs_host(const uint64_t* keys_in, int64_t n, int key_bits, uint64_t* keys_out, uint32_t* idx_out, float* ms);
 
 }  // namespace nbody

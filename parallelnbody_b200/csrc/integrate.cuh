@@ -66,21 +66,6 @@ kick_drift_kernel(const int n, const float dt, float4* __restrict__ posm, float4
 // Non-negative floats order like their bit patterns, so the cross-CTA combine is an integer atomicMax.
 // Also produces the tight bounding box (min/max per axis) used by the non-reference root mode; box6 holds
 // order-preserving uint keys (see float_to_ordered) so the same atomics work for signed values.
-__device__ __forceinline__ uint32_t float_to_ordered(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__host__ __device__ inline float ordered_to_float(uint32_t k) {
-  const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-#ifdef __CUDA_ARCH__
-  return __uint_as_float(u);
-#else
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-#endif
-}
-
 // out[0] = absmax bits; out[1..3] = ordered min x,y,z ; out[4..6] = ordered max x,y,z.
 // Initialise out = {0, ~0,~0,~0, 0,0,0} before the launch.
 __global__ void __launch_bounds__(256)

@@ -84,7 +84,10 @@ struct nbody_sim {
   float4* d_vel = nullptr;   int64_t cap_vel = 0;
   float4* d_acc = nullptr;   int64_t cap_acc = 0;
   float4* d_partial = nullptr; int64_t cap_partial = 0;
-  int32_t* d_ids = nullptr;  int64_t cap_ids = 0;     // original index of local body i (BH reorders bodies)
+  int32_t* d_ids = nullptr;  int64_t cap_ids = 0;     // original index of body i (BH reorders bodies every step)
+  float4* d_posm2 = nullptr; int64_t cap_posm2 = 0;   // BH: destination of the next Morton reordering (swapped each build)
+  float4* d_vel2 = nullptr;  int64_t cap_vel2 = 0;
+  int32_t* d_ids2 = nullptr; int64_t cap_ids2 = 0;
   uint8_t* d_stage = nullptr; int64_t cap_stage = 0;
   uint32_t* d_box = nullptr;   // 8 words: absmax, min xyz, max xyz
   double* d_energy = nullptr;  // 2 doubles
@@ -92,14 +95,24 @@ struct nbody_sim {
 
   Comm* comm = nullptr;
   DirectPlan plan;
-  BHState bh;
+  BHState tree;
 
   // timing of the last call
   float ms_call = 0, ms_force = 0, ms_build = 0, ms_integrate = 0, ms_comm = 0;
   double interactions = 0;
   float cube_size = 0;
 
-  float4* posm_local() { return d_posm + (cfg.method == NBODY_DIRECT ? local_begin : 0); }
+  // Direct sum: posm holds all N sources (this rank's slice at local_begin), vel / acc hold the local slice only.
+  // Barnes-Hut: every array holds all N bodies in Morton order; this rank integrates the slice at local_begin.
+  bool bh() const { return cfg.method == NBODY_BARNES_HUT; }
+  float4* posm_local() { return d_posm + local_begin; }
+  float4* vel_local() { return d_vel + (bh() ? local_begin : 0); }
+  float4* acc_local() { return d_acc + (bh() ? local_begin : 0); }
+  int32_t* ids_local() { return d_ids + (bh() ? local_begin : 0); }
+  // which bodies a set_* call uploads to this rank, and where they land
+  int64_t load_begin() const { return bh() ? 0 : local_begin; }
+  int64_t load_count() const { return bh() ? n_global : n_local; }
+  float4* posm_load() { return d_posm + load_begin(); }
 };
 
 namespace {
@@ -148,12 +161,19 @@ int reserve_state(nbody_sim* s) {
     const int64_t need_src = std::max<int64_t>(s->plan.n_src_pad, s->n_per * s->cfg.world);
     NB_TRY(dev_reserve(&s->d_posm, &s->cap_posm, need_src, s->stream));
     NB_TRY(dev_reserve(&s->d_partial, &s->cap_partial, (int64_t)s->plan.jsplit * s->plan.n_tgt_pad, s->stream));
+    NB_TRY(dev_reserve(&s->d_vel, &s->cap_vel, std::max<int64_t>(s->n_local, 1), s->stream));
+    NB_TRY(dev_reserve(&s->d_acc, &s->cap_acc, std::max<int64_t>(s->n_local, 1), s->stream));
+    NB_TRY(dev_reserve(&s->d_ids, &s->cap_ids, std::max<int64_t>(s->n_local, 1), s->stream));
   } else {
-    NB_TRY(dev_reserve(&s->d_posm, &s->cap_posm, std::max<int64_t>(s->n_local, 1), s->stream));
+    const int64_t total = std::max<int64_t>(s->n_per * s->cfg.world, 1);   // padded so the slices all-gather in place
+    NB_TRY(dev_reserve(&s->d_posm, &s->cap_posm, total, s->stream));
+    NB_TRY(dev_reserve(&s->d_vel, &s->cap_vel, total, s->stream));
+    NB_TRY(dev_reserve(&s->d_acc, &s->cap_acc, total, s->stream));
+    NB_TRY(dev_reserve(&s->d_ids, &s->cap_ids, total, s->stream));
+    NB_TRY(dev_reserve(&s->d_posm2, &s->cap_posm2, total, s->stream));
+    NB_TRY(dev_reserve(&s->d_vel2, &s->cap_vel2, total, s->stream));
+    NB_TRY(dev_reserve(&s->d_ids2, &s->cap_ids2, total, s->stream));
   }
-  NB_TRY(dev_reserve(&s->d_vel, &s->cap_vel, std::max<int64_t>(s->n_local, 1), s->stream));
-  NB_TRY(dev_reserve(&s->d_acc, &s->cap_acc, std::max<int64_t>(s->n_local, 1), s->stream));
-  NB_TRY(dev_reserve(&s->d_ids, &s->cap_ids, std::max<int64_t>(s->n_local, 1), s->stream));
   (void)n;
   return 0;
 }
@@ -208,13 +228,16 @@ int launch_direct(nbody_sim* s) {
 int launch_cube_size(nbody_sim* s) {
   static const uint32_t init[8] = {0u, ~0u, ~0u, ~0u, 0u, 0u, 0u, 0u};
   NB_CUDA(cudaMemcpyAsync(s->d_box, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
-  if (s->n_local > 0) {
-    const int blocks = (int)std::min<int64_t>(ceil_div(s->n_local, 256), kNumSMsB200 * 8);
-    cube_size_kernel<<<blocks, 256, 0, s->stream>>>(s->posm_local(), (int)s->n_local, s->d_box);
+  // Barnes-Hut keeps all N bodies on every rank: reduce over them locally, no collective
+  const float4* src = s->bh() ? s->d_posm : s->posm_local();
+  const int64_t cnt = s->bh() ? s->n_global : s->n_local;
+  if (cnt > 0) {
+    const int blocks = (int)std::min<int64_t>(ceil_div(cnt, 256), kNumSMsB200 * 8);
+    cube_size_kernel<<<blocks, 256, 0, s->stream>>>(src, (int)cnt, s->d_box);
     s->launches++;
     NB_CUDA(cudaGetLastError());
   }
-  if (s->comm) {
+  if (s->comm && !s->bh()) {
     NB_TRY(s->comm->all_reduce_u32_max(s->d_box, 1, s->stream));
     NB_TRY(s->comm->all_reduce_u32_min(s->d_box + 1, 3, s->stream));
     NB_TRY(s->comm->all_reduce_u32_max(s->d_box + 4, 3, s->stream));
@@ -247,19 +270,32 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
     BHParams bp;
     bp.G = s->cfg.G; bp.eps2 = s->cfg.eps * s->cfg.eps; bp.theta = s->cfg.theta;
     bp.leaf_size = std::max(1, s->cfg.leaf_size); bp.reference_root = s->cfg.reference_root != 0;
+    bp.mac = s->cfg.mac;
     double launches = 0;
-    NB_TRY(bh_build(s->bh, bp, &s->d_posm, &s->d_vel, &s->d_ids, (int)s->n_local, s->d_box, s->stream, &launches));
+    // Morton reordering of ALL bodies (identical on every rank: same data, stable sort), tree + monopoles
+    NB_TRY(bh_build(s->tree, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_global, s->d_box,
+                    s->stream, &launches));
+    std::swap(s->d_posm, s->d_posm2); std::swap(s->cap_posm, s->cap_posm2);
+    std::swap(s->d_vel, s->d_vel2);   std::swap(s->cap_vel, s->cap_vel2);
+    std::swap(s->d_ids, s->d_ids2);   std::swap(s->cap_ids, s->cap_ids2);
     s->ids_identity = false;
     if (ev) NB_CUDA(cudaEventRecord(ev[1], s->stream));
-    NB_TRY(bh_forces(s->bh, bp, s->d_posm, s->d_acc, (int)s->n_local, s->stream, &launches));
+    // this rank walks and integrates its slice of the Morton order (a compact spatial domain)
+    const int t0 = (int)s->local_begin, t1 = (int)(s->local_begin + s->n_local);
+    NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_global, t0, t1, s->stream, &launches));
     s->launches += launches;
     if (ev) NB_CUDA(cudaEventRecord(ev[2], s->stream));
     if (integrate && s->n_local > 0) {
-      kick_drift_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>((int)s->n_local, dt, s->d_posm, s->d_vel, s->d_acc);
+      kick_drift_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>((int)s->n_local, dt, s->posm_local(), s->vel_local(), s->acc_local());
       s->launches++;
       NB_CUDA(cudaGetLastError());
     }
-    if (ev) { NB_CUDA(cudaEventRecord(ev[3], s->stream)); NB_CUDA(cudaEventRecord(ev[4], s->stream)); }
+    if (ev) NB_CUDA(cudaEventRecord(ev[3], s->stream));
+    if (integrate && s->comm) {
+      NB_TRY(s->comm->all_gather_f32_inplace(reinterpret_cast<float*>(s->d_posm), (size_t)s->n_per * 4, s->stream));
+      NB_TRY(s->comm->all_gather_f32_inplace(reinterpret_cast<float*>(s->d_vel), (size_t)s->n_per * 4, s->stream));
+    }
+    if (ev) NB_CUDA(cudaEventRecord(ev[4], s->stream));
   }
   if (integrate) s->steps++;
   return 0;
@@ -294,7 +330,7 @@ int run_steps(nbody_sim* s, float dt, int nsteps, bool integrate, bool sync) {
     const float f = (float)nsteps / (float)timed;
     s->ms_build *= f; s->ms_force *= f; s->ms_integrate *= f; s->ms_comm *= f;
   }
-  if (s->cfg.method == NBODY_BARNES_HUT) NB_TRY(bh_fetch_stats(s->bh, s->stream, &s->interactions));
+  if (s->cfg.method == NBODY_BARNES_HUT) NB_TRY(bh_fetch_stats(s->tree, s->stream, &s->interactions));
   return 0;
 }
 
@@ -302,11 +338,11 @@ int stage_reserve(nbody_sim* s, int64_t bytes) { return dev_reserve(&s->d_stage,
 
 int finish_set(nbody_sim* s) {
   s->ids_identity = true;
-  if (s->cfg.method == NBODY_BARNES_HUT && s->n_local > 0) {
-    bh_iota(s->d_ids, (int)s->n_local, (int)s->local_begin, s->stream);
+  if (s->bh()) {
+    bh_iota(s->d_ids, (int)s->n_global, 0, s->stream);
     s->launches++;
   }
-  bh_reset(s->bh);
+  bh_reset(s->tree, s->stream);
   NB_TRY(publish_positions(s));
   NB_CUDA(cudaStreamSynchronize(s->stream));
   s->initialized = true;
@@ -319,7 +355,7 @@ int get_array(nbody_sim* s, int what, float* out4, int64_t n) {
   if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
   if (!out4 || n < s->n_global) return invalid("output buffer is NULL or smaller than n_global bodies");
   NB_CUDA(cudaSetDevice(s->cfg.device));
-  const float4* src = what == 0 ? s->posm_local() : what == 1 ? s->d_vel : s->d_acc;
+  const float4* src = what == 0 ? s->posm_local() : what == 1 ? s->vel_local() : s->acc_local();
   if (s->n_local == 0) return 0;
   if (s->ids_identity) {
     NB_CUDA(cudaMemcpyAsync(out4 + 4 * s->local_begin, src, (size_t)s->n_local * 16, cudaMemcpyDeviceToHost, s->stream));
@@ -329,7 +365,7 @@ int get_array(nbody_sim* s, int what, float* out4, int64_t n) {
   std::vector<float4> tmp((size_t)s->n_local);
   std::vector<int32_t> ids((size_t)s->n_local);
   NB_CUDA(cudaMemcpyAsync(tmp.data(), src, (size_t)s->n_local * 16, cudaMemcpyDeviceToHost, s->stream));
-  NB_CUDA(cudaMemcpyAsync(ids.data(), s->d_ids, (size_t)s->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
+  NB_CUDA(cudaMemcpyAsync(ids.data(), s->ids_local(), (size_t)s->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
   NB_CUDA(cudaStreamSynchronize(s->stream));
   for (int64_t i = 0; i < s->n_local; i++) memcpy(out4 + 4 * (size_t)ids[(size_t)i], &tmp[(size_t)i], 16);
   return 0;
@@ -357,6 +393,7 @@ int nbody_config_default(nbody_config* cfg) {
   cfg->world = 1;
   cfg->leaf_size = 16;
   cfg->reference_root = 0;
+  cfg->mac = 0;
   return NBODY_OK;
 }
 
@@ -372,7 +409,7 @@ int nbody_create(nbody_sim** out, const nbody_config* cfg) {
   if (cfg->method != NBODY_DIRECT && cfg->method != NBODY_BARNES_HUT) return invalid("unknown method");
   if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return invalid("bad rank/world");
   if (!(cfg->eps >= 0.f) || !(cfg->theta >= 0.f)) return invalid("eps and theta must be >= 0");
-  if (cfg->method == NBODY_BARNES_HUT && cfg->world > 1) return invalid("multi-GPU Barnes-Hut is not available in this build");
+  if (cfg->mac != 0 && cfg->mac != 1) return invalid("mac must be 0 (group) or 1 (per body, reference rule)");
   NB_TRY(check_device(cfg->device));
   nbody_sim* s = new nbody_sim();
   s->cfg = *cfg;
@@ -394,7 +431,8 @@ void nbody_destroy(nbody_sim* s) {
   cudaSetDevice(s->cfg.device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   delete s->comm;
-  bh_free(s->bh);
+  bh_free(s->tree);
+  cudaFree(s->d_posm2); cudaFree(s->d_vel2); cudaFree(s->d_ids2);
   cudaFree(s->d_posm); cudaFree(s->d_vel); cudaFree(s->d_acc); cudaFree(s->d_partial); cudaFree(s->d_ids);
   cudaFree(s->d_stage); cudaFree(s->d_box); cudaFree(s->d_energy);
   for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
@@ -410,8 +448,8 @@ int nbody_create_space_points(nbody_sim* s, int64_t n, float size, uint64_t seed
   NB_CUDA(cudaSetDevice(s->cfg.device));
   partition(s, n);
   NB_TRY(reserve_state(s));
-  if (s->n_local > 0) {
-    space_points_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(seed, s->local_begin, (int)s->n_local, size, s->posm_local(), s->d_vel, s->d_acc);
+  if (s->load_count() > 0) {
+    space_points_kernel<<<(unsigned)ceil_div(s->load_count(), 256), 256, 0, s->stream>>>(seed, s->load_begin(), (int)s->load_count(), size, s->posm_load(), s->d_vel, s->d_acc);
     s->launches++;
     NB_CUDA(cudaGetLastError());
   }
@@ -427,11 +465,11 @@ int nbody_set_particles_aos(nbody_sim* s, const void* particles, int64_t n, size
   NB_CUDA(cudaSetDevice(s->cfg.device));
   partition(s, n);
   NB_TRY(reserve_state(s));
-  if (s->n_local > 0) {
-    const size_t bytes = (size_t)s->n_local * stride;
+  if (s->load_count() > 0) {
+    const size_t bytes = (size_t)s->load_count() * stride;
     NB_TRY(stage_reserve(s, (int64_t)bytes));
-    NB_CUDA(cudaMemcpyAsync(s->d_stage, (const uint8_t*)particles + (size_t)s->local_begin * stride, bytes, cudaMemcpyHostToDevice, s->stream));
-    aos_to_soa_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(s->d_stage, stride, 0, (int)s->n_local, s->posm_local(), s->d_vel, s->d_acc);
+    NB_CUDA(cudaMemcpyAsync(s->d_stage, (const uint8_t*)particles + (size_t)s->load_begin() * stride, bytes, cudaMemcpyHostToDevice, s->stream));
+    aos_to_soa_kernel<<<(unsigned)ceil_div(s->load_count(), 256), 256, 0, s->stream>>>(s->d_stage, stride, 0, (int)s->load_count(), s->posm_load(), s->d_vel, s->d_acc);
     s->launches++;
     NB_CUDA(cudaGetLastError());
   }
@@ -445,11 +483,12 @@ int nbody_set_bodies(nbody_sim* s, const float* posm4, const float* vel4, int64_
   NB_CUDA(cudaSetDevice(s->cfg.device));
   partition(s, n);
   NB_TRY(reserve_state(s));
-  if (s->n_local > 0) {
-    NB_CUDA(cudaMemcpyAsync(s->posm_local(), posm4 + 4 * s->local_begin, (size_t)s->n_local * 16, cudaMemcpyHostToDevice, s->stream));
-    if (vel4) NB_CUDA(cudaMemcpyAsync(s->d_vel, vel4 + 4 * s->local_begin, (size_t)s->n_local * 16, cudaMemcpyHostToDevice, s->stream));
-    else NB_CUDA(cudaMemsetAsync(s->d_vel, 0, (size_t)s->n_local * 16, s->stream));
-    NB_CUDA(cudaMemsetAsync(s->d_acc, 0, (size_t)s->n_local * 16, s->stream));
+  if (s->load_count() > 0) {
+    const size_t bytes = (size_t)s->load_count() * 16;
+    NB_CUDA(cudaMemcpyAsync(s->posm_load(), posm4 + 4 * s->load_begin(), bytes, cudaMemcpyHostToDevice, s->stream));
+    if (vel4) NB_CUDA(cudaMemcpyAsync(s->d_vel, vel4 + 4 * s->load_begin(), bytes, cudaMemcpyHostToDevice, s->stream));
+    else NB_CUDA(cudaMemsetAsync(s->d_vel, 0, bytes, s->stream));
+    NB_CUDA(cudaMemsetAsync(s->d_acc, 0, bytes, s->stream));
   }
   return finish_set(s);
 }
@@ -461,7 +500,7 @@ int nbody_clean_particles(nbody_sim* s) {
   s->initialized = false;  // OctreeSearch.cpp:93
   s->n_global = s->n_local = 0;
   s->steps = 0;
-  bh_reset(s->bh);
+  bh_reset(s->tree, s->stream);
   return NBODY_OK;
 }
 
@@ -524,7 +563,7 @@ int nbody_get_particles_aos(nbody_sim* s, void* particles, int64_t n, size_t str
   if (s->n_local == 0) return NBODY_OK;
   const size_t bytes = (size_t)s->n_local * 40;
   NB_TRY(stage_reserve(s, (int64_t)bytes));
-  soa_to_aos_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(s->posm_local(), s->d_vel, s->d_acc, (int)s->n_local, reinterpret_cast<float*>(s->d_stage));
+  soa_to_aos_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(s->posm_local(), s->vel_local(), s->acc_local(), (int)s->n_local, reinterpret_cast<float*>(s->d_stage));
   s->launches++;
   NB_CUDA(cudaGetLastError());
   uint8_t* dst = (uint8_t*)particles;
@@ -538,7 +577,7 @@ int nbody_get_particles_aos(nbody_sim* s, void* particles, int64_t n, size_t str
   NB_CUDA(cudaMemcpyAsync(tmp.data(), s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
   if (!s->ids_identity) {
     ids.resize((size_t)s->n_local);
-    NB_CUDA(cudaMemcpyAsync(ids.data(), s->d_ids, (size_t)s->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
+    NB_CUDA(cudaMemcpyAsync(ids.data(), s->ids_local(), (size_t)s->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
   }
   NB_CUDA(cudaStreamSynchronize(s->stream));
   for (int64_t i = 0; i < s->n_local; i++) {
@@ -560,7 +599,7 @@ int nbody_get_local_ids(nbody_sim* s, int64_t* ids, int64_t cap, int64_t* n_loca
   }
   NB_CUDA(cudaSetDevice(s->cfg.device));
   std::vector<int32_t> h((size_t)s->n_local);
-  NB_CUDA(cudaMemcpyAsync(h.data(), s->d_ids, (size_t)s->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
+  NB_CUDA(cudaMemcpyAsync(h.data(), s->ids_local(), (size_t)s->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
   NB_CUDA(cudaStreamSynchronize(s->stream));
   for (int64_t i = 0; i < s->n_local; i++) ids[i] = h[(size_t)i];
   return NBODY_OK;
@@ -576,6 +615,7 @@ int nbody_set_param(nbody_sim* s, int32_t which, double v) {
     case NBODY_PARAM_LEAF_SIZE: if (v < 1 || v > 64) return invalid("leaf_size must be in [1, 64]"); s->cfg.leaf_size = (int)v; return NBODY_OK;
     case NBODY_PARAM_REFERENCE_ROOT: s->cfg.reference_root = v != 0; return NBODY_OK;
     case NBODY_PARAM_SHOW_OCTREE: s->show_octree = v != 0; return NBODY_OK;
+    case NBODY_PARAM_MAC: if (v != 0 && v != 1) return invalid("mac must be 0 or 1"); s->cfg.mac = (int)v; return NBODY_OK;
     case NBODY_PARAM_METHOD: return invalid("method is fixed at nbody_create (device layout depends on it)");
     default: return invalid("unknown or read-only parameter");
   }
@@ -593,6 +633,7 @@ int nbody_get_param(nbody_sim* s, int32_t which, double* v) {
     case NBODY_PARAM_REFERENCE_ROOT: *v = s->cfg.reference_root; return NBODY_OK;
     case NBODY_PARAM_SHOW_OCTREE: *v = s->show_octree; return NBODY_OK;
     case NBODY_PARAM_INITIALIZED: *v = s->initialized; return NBODY_OK;
+    case NBODY_PARAM_MAC: *v = s->cfg.mac; return NBODY_OK;
     default: return invalid("unknown parameter");
   }
 }
@@ -603,12 +644,9 @@ int nbody_energy(nbody_sim* s, double* ke, double* pe) {
   NB_CUDA(cudaSetDevice(s->cfg.device));
   NB_CUDA(cudaMemsetAsync(s->d_energy, 0, 2 * sizeof(double), s->stream));
   if (s->n_local > 0) {
-    const float4* src = s->d_posm;
-    const int n_src = (int)(s->cfg.method == NBODY_DIRECT ? s->n_global : s->n_local);
-    // global index of local body i for the self-pair exclusion: direct = slice offset; BH (single GPU, reordered
-    // bodies) = position in the local array, which is also its position in the source array.
-    const int64_t first = s->cfg.method == NBODY_DIRECT ? s->local_begin : 0;
-    energy_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(src, n_src, s->posm_local(), s->d_vel, (int)s->n_local, first, s->cfg.G, s->cfg.eps * s->cfg.eps, s->d_energy);
+    // sources = all N bodies (both methods keep them in d_posm); local body i sits at source index local_begin + i,
+    // which is what the self-pair exclusion needs
+    energy_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(s->d_posm, (int)s->n_global, s->posm_local(), s->vel_local(), (int)s->n_local, s->local_begin, s->cfg.G, s->cfg.eps * s->cfg.eps, s->d_energy);
     s->launches++;
     NB_CUDA(cudaGetLastError());
   }
@@ -632,9 +670,9 @@ int nbody_stats_get(nbody_sim* s, nbody_stats* out) {
   out->ms_integrate = s->ms_integrate; out->ms_comm = s->ms_comm;
   out->cube_size = s->cube_size;
   out->jsplit = s->plan.jsplit; out->i_per_thread = s->plan.i_per_thread;
-  out->tree_nodes = s->bh.n_nodes_host; out->tree_depth = s->bh.depth_host;
-  memcpy(out->root_com, s->bh.root_com_host, sizeof(out->root_com));
-  out->root_mass = s->bh.root_mass_host;
+  out->tree_nodes = s->tree.n_nodes_host; out->tree_depth = s->tree.depth_host;
+  memcpy(out->root_com, s->tree.root_com_host, sizeof(out->root_com));
+  out->root_mass = s->tree.root_mass_host;
   return NBODY_OK;
 }
 
@@ -643,16 +681,33 @@ int nbody_octree_boxes(nbody_sim* s, float* boxes7, int64_t cap, int64_t* n_boxe
   if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
   if (s->cfg.method != NBODY_BARNES_HUT) return invalid("octree boxes exist only for the Barnes-Hut method");
   NB_CUDA(cudaSetDevice(s->cfg.device));
-  return bh_leaf_boxes(s->bh, s->d_posm, (int)s->n_local, boxes7, cap, n_boxes, s->stream);
+  return bh_leaf_boxes(s->tree, s->d_posm, (int)s->n_global, boxes7, cap, n_boxes, s->stream);
 }
 
 int nbody_device_ptrs(nbody_sim* s, void** posm4, void** vel4, void** acc4) {
   if (!s) return invalid("sim is NULL");
   if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
   if (posm4) *posm4 = s->posm_local();
-  if (vel4) *vel4 = s->d_vel;
-  if (acc4) *acc4 = s->d_acc;
+  if (vel4) *vel4 = s->vel_local();
+  if (acc4) *acc4 = s->acc_local();
   return NBODY_OK;
+}
+
+int nbody_octree_nodes(nbody_sim* s, float* com4, int32_t* meta4, int32_t* range2, uint64_t* keys, int64_t cap_nodes,
+                       int64_t cap_keys, int64_t* n_nodes) {
+  if (!s) return invalid("sim is NULL");
+  if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
+  if (s->cfg.method != NBODY_BARNES_HUT) return invalid("the octree exists only for the Barnes-Hut method");
+  NB_CUDA(cudaSetDevice(s->cfg.device));
+  return bh_read_tree(s->tree, com4, meta4, range2, keys, cap_nodes, cap_keys, n_nodes, s->stream);
+}
+
+int nbody_sort_pairs_u64(int32_t device, const uint64_t* keys_in, int64_t n, int32_t key_bits, uint64_t* keys_out,
+                         uint32_t* idx_out, float* ms) {
+  if (!keys_in) return invalid("keys_in is NULL");
+  if (key_bits < 1 || key_bits > 64) return invalid("key_bits must be in [1, 64]");
+  NB_TRY(check_device(device));
+  return sort_pairs_host(keys_in, n, key_bits, keys_out, idx_out, ms);
 }
 
 // ---- FP32 peak probe ----------------------------------------------------------------------------------

@@ -1,0 +1,190 @@
+// K5 - device LSD radix sort of (64-bit Morton key, 32-bit body index) pairs, hand-written for sm_100a.
+//
+// Replaces the ordering that the reference obtains implicitly by inserting bodies one at a time into its pointer
+// octree (Octree::Add, /root/reference/Source/NBody/OctreeSearch.h:60-81): sorting the bodies along the Morton curve
+// makes every octree cell a contiguous index range.
+//
+// 8 passes of 8 bits. Per pass: (1) per-CTA digit histogram, (2) exclusive scan of the digit-major table
+// hist[digit][cta] (gives every CTA its global base per digit), (3) stable scatter: each warp ranks its keys with
+// __match_any_sync (lane order == memory order), warp counts are prefixed across the CTA's warps, and each key goes to
+// base[digit] + rank. All HBM-bound: per pass 8 B key read (hist) + 12 B read + 12 B write (scatter) per body.
+#pragma once
+#include "common.cuh"
+
+namespace nbody {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;                               // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;        // 2048 keys per CTA
+constexpr int kSortWarps = kSortThreads / 32;
+
+// ---- exclusive scan of uint32 (three small kernels; n up to 2^31) --------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  return v;
+}
+
+// Block-wide exclusive scan of one value per thread (256 threads); returns the exclusive prefix, *total = block sum.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t wsum[kScanThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t inc = warp_incl_scan(v);
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = lane < kScanThreads / 32 ? wsum[lane] : 0u;
+    s = warp_incl_scan(s);
+    if (lane < kScanThreads / 32) wsum[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t base = w ? wsum[w - 1] : 0u;
+  *total = wsum[kScanThreads / 32 - 1];
+  __syncthreads();
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_sums_kernel(const uint32_t* __restrict__ in, const int64_t n, uint32_t* __restrict__ tile_sums) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) if (base + k < n) s += in[base + k];
+  uint32_t total;
+  block_excl_scan(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// One CTA: in-place exclusive scan of m tile sums (m is small: n / 2048).
+__global__ void __launch_bounds__(kScanThreads)
+scan_spine_kernel(uint32_t* __restrict__ tile_sums, const int64_t m) {
+  uint32_t carry = 0;
+  for (int64_t base = 0; base < m; base += kScanThreads) {
+    const int64_t i = base + threadIdx.x;
+    const uint32_t v = i < m ? tile_sums[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan(v, &total);
+    if (i < m) tile_sums[i] = carry + ex;
+    carry += total;
+  }
+}
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(uint32_t* __restrict__ data, const int64_t n, const uint32_t* __restrict__ tile_sums) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems], s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) { v[k] = base + k < n ? data[base + k] : 0u; s += v[k]; }
+  uint32_t total;
+  uint32_t ex = block_excl_scan(s, &total) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) { if (base + k < n) data[base + k] = ex; ex += v[k]; }
+}
+
+// In-place exclusive scan; tile_sums must hold ceil(n / kScanTile) words. 3 launches.
+inline void exclusive_scan_u32(uint32_t* data, int64_t n, uint32_t* tile_sums, cudaStream_t s, double* launches) {
+  const int64_t tiles = ceil_div(n, kScanTile);
+  scan_tile_sums_kernel<<<(unsigned)tiles, kScanThreads, 0, s>>>(data, n, tile_sums);
+  scan_spine_kernel<<<1, kScanThreads, 0, s>>>(tile_sums, tiles);
+  scan_apply_kernel<<<(unsigned)tiles, kScanThreads, 0, s>>>(data, n, tile_sums);
+  if (launches) *launches += 3;
+}
+
+// ---- radix pass ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const uint64_t* __restrict__ keys, const int n, const int shift, uint32_t* __restrict__ hist,
+                  const int nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int k = 0; k < kSortItems; k++) {
+    const int i = base + k * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// hist must already hold the exclusive scan of the digit-major table. idx_in == nullptr: payload = position (pass 0).
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, const int n,
+                     const int shift, const uint32_t* __restrict__ hist, const int nblocks,
+                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+  __shared__ uint32_t wcount[kSortWarps][256];
+  __shared__ uint32_t dbase[256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kSortWarps; k++) wcount[k][threadIdx.x] = 0;
+  __syncthreads();
+  // warp w owns the contiguous segment [seg, seg + 32 * kSortItems); round r, lane l -> seg + 32 r + l
+  const int seg = blockIdx.x * kSortTile + w * (32 * kSortItems);
+  uint64_t key[kSortItems];
+  uint32_t rank[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; r++) {
+    const int i = seg + 32 * r + lane;
+    const bool live = i < n;
+    key[r] = live ? keys_in[i] : ~0ull;
+    const uint32_t d = live ? ((uint32_t)(key[r] >> shift) & 255u) : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    uint32_t prev = 0;
+    if (live) prev = wcount[w][d];
+    __syncwarp();
+    if (live && before == 0) wcount[w][d] = prev + __popc(peers);
+    __syncwarp();
+    rank[r] = prev + before;
+  }
+  __syncthreads();
+  {  // thread d: prefix the warp counts of digit d over the CTA's warps, fetch the global base
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < kSortWarps; k++) { const uint32_t t = wcount[k][threadIdx.x]; wcount[k][threadIdx.x] = run; run += t; }
+    dbase[threadIdx.x] = hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortItems; r++) {
+    const int i = seg + 32 * r + lane;
+    if (i < n) {
+      const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+      const uint32_t pos = dbase[d] + wcount[w][d] + rank[r];
+      keys_out[pos] = key[r];
+      idx_out[pos] = idx_in ? idx_in[i] : (uint32_t)i;
+    }
+  }
+}
+
+struct RadixSortBuffers {
+  uint64_t* keys[2] = {nullptr, nullptr};
+  uint32_t* idx[2] = {nullptr, nullptr};
+  uint32_t* hist = nullptr;       // 256 * nblocks
+  uint32_t* tile_sums = nullptr;  // ceil(256 * nblocks / kScanTile)
+};
+
+// Sorts keys[0] (payload = iota) over `key_bits` low bits; the result is in keys[out], idx[out] (returned index).
+inline int radix_sort_pairs(RadixSortBuffers& b, int n, int key_bits, cudaStream_t s, double* launches) {
+  const int nblocks = (int)ceil_div(n, kSortTile);
+  int cur = 0;
+  const int passes = (key_bits + 7) / 8;
+  for (int p = 0; p < passes; p++) {
+    const int shift = 8 * p;
+    radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(b.keys[cur], n, shift, b.hist, nblocks);
+    if (launches) *launches += 1;
+    exclusive_scan_u32(b.hist, (int64_t)256 * nblocks, b.tile_sums, s, launches);
+    radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(b.keys[cur], p == 0 ? nullptr : b.idx[cur], n, shift, b.hist, nblocks,
+                                                           b.keys[cur ^ 1], b.idx[cur ^ 1]);
+    if (launches) *launches += 1;
+    cur ^= 1;
+  }
+  return cur;
+}
+
+}  // namespace nbody
