@@ -104,7 +104,8 @@ def make_ic(name: str, n: int, seed: int = 1234):
 
 
 def dist_env():
-    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    from parallelnbody_b200.launch import dist_env as f
+    return f()
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -221,14 +222,11 @@ def run_ours(args, wl):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    from parallelnbody_b200 import launch
     uid = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            t.copy_(torch.frombuffer(bytearray(P.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(t, 0)
-        uid = bytes(t.cpu().numpy().tobytes())
+        uid = launch.broadcast_unique_id(P.comm_unique_id, dist, device="cuda")
 
     def barrier():
         if world > 1:
@@ -236,18 +234,10 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return launch.reduce_scalar(x, dist, "max", device="cuda") if world > 1 else x
 
     def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return launch.reduce_scalar(x, dist, "sum", device="cuda") if world > 1 else x
 
     posm, vel = make_ic(icname, n)
     meth = P.METHOD_DIRECT if method == "direct" else P.METHOD_BARNES_HUT

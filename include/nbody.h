@@ -72,7 +72,9 @@ typedef struct nbody_config {
                              reference's per-body test would open); 1 = per body, exactly OctreeSearch.h:100-107 incl. the
                              visiting order (parity mode, slower) */
   int32_t reserved[4];
-  uint8_t nccl_unique_id[128]; /* multi-GPU: the ncclUniqueId from nbody_comm_unique_id on rank 0 */
+  uint8_t nccl_unique_id[128]; /* multi-GPU: the ncclUniqueId from nbody_comm_unique_id on rank 0. All zeros with world > 1 =
+                                  an EMULATED rank: no communicator; the handle evaluates its slice of the bodies given by
+                                  nbody_set_bodies and never exchanges (several ranks can then be checked on one GPU) */
   void* stream;           /* optional cudaStream_t to run on (NULL = the handle creates its own) */
 } nbody_config;
 

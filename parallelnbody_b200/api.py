@@ -174,7 +174,8 @@ class OctreeSearch:
         cfg.mac = mac
         if world > 1:
             if nccl_unique_id is None or len(nccl_unique_id) != 128:
-                raise NBodyError(-1, "world > 1 needs the 128-byte nccl_unique_id broadcast from rank 0")
+                raise NBodyError(-1, "world > 1 needs the 128-byte nccl_unique_id broadcast from rank 0 "
+                                     "(or 128 zero bytes for an emulated rank)")
             C.memmove(cfg.nccl_unique_id, nccl_unique_id, 128)
         cfg.stream = stream
         self._h = C.c_void_p()

@@ -92,6 +92,7 @@ struct nbody_sim {
   uint32_t* d_box = nullptr;   // 8 words: absmax, min xyz, max xyz
   double* d_energy = nullptr;  // 2 doubles
   bool ids_identity = true;
+  bool emulated = false;   // world > 1 without a communicator (all-zero NCCL id): slices only, exchanges are the caller's job
 
   Comm* comm = nullptr;
   DirectPlan plan;
@@ -420,7 +421,12 @@ int nbody_create(nbody_sim** out, const nbody_config* cfg) {
   NB_C(NB_CUDA(cudaEventCreate(&s->ev1)));
   NB_C(NB_CUDA(cudaMalloc((void**)&s->d_box, 8 * sizeof(uint32_t))));
   NB_C(NB_CUDA(cudaMalloc((void**)&s->d_energy, 2 * sizeof(double))));
-  if (cfg->world > 1) NB_C(NB_TRY(Comm::create(&s->comm, cfg->nccl_unique_id, cfg->rank, cfg->world)));
+  if (cfg->world > 1) {
+    bool zero_id = true;
+    for (int k = 0; k < 128; k++) zero_id = zero_id && cfg->nccl_unique_id[k] == 0;
+    if (zero_id) s->emulated = true;
+    else NB_C(NB_TRY(Comm::create(&s->comm, cfg->nccl_unique_id, cfg->rank, cfg->world)));
+  }
 #undef NB_C
   *out = s;
   return NBODY_OK;
@@ -445,6 +451,7 @@ void nbody_destroy(nbody_sim* s) {
 int nbody_create_space_points(nbody_sim* s, int64_t n, float size, uint64_t seed) {
   if (!s) return invalid("sim is NULL");
   if (n < 1 || n > (int64_t)1 << 30) return invalid("N must be in [1, 2^30] (the reference indexes Particles[0], OctreeSearch.cpp:68)");
+  if (s->emulated) return invalid("an emulated rank (world > 1, all-zero NCCL id) takes its bodies from nbody_set_bodies only");
   NB_CUDA(cudaSetDevice(s->cfg.device));
   partition(s, n);
   NB_TRY(reserve_state(s));
@@ -462,6 +469,7 @@ int nbody_set_particles_aos(nbody_sim* s, const void* particles, int64_t n, size
   if (n < 1 || n > (int64_t)1 << 30) return invalid("n must be in [1, 2^30]");
   if (!particles) return invalid("particles is NULL");
   if (stride < sizeof(nbody_particle) || stride % 4) return invalid("stride must be >= 40 and a multiple of 4");
+  if (s->emulated) return invalid("an emulated rank (world > 1, all-zero NCCL id) takes its bodies from nbody_set_bodies only");
   NB_CUDA(cudaSetDevice(s->cfg.device));
   partition(s, n);
   NB_TRY(reserve_state(s));
@@ -489,6 +497,8 @@ int nbody_set_bodies(nbody_sim* s, const float* posm4, const float* vel4, int64_
     if (vel4) NB_CUDA(cudaMemcpyAsync(s->d_vel, vel4 + 4 * s->load_begin(), bytes, cudaMemcpyHostToDevice, s->stream));
     else NB_CUDA(cudaMemsetAsync(s->d_vel, 0, bytes, s->stream));
     NB_CUDA(cudaMemsetAsync(s->d_acc, 0, bytes, s->stream));
+    // an emulated rank has no communicator to gather the other slices: take all sources from the caller
+    if (s->emulated && !s->bh()) NB_CUDA(cudaMemcpyAsync(s->d_posm, posm4, (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
   }
   return finish_set(s);
 }
