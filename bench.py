@@ -40,7 +40,10 @@ WORKLOADS = {
     "plummer_1m_direct": ("plummer", 1 << 20, "direct", 0.01, 0.0, 1e-3),
     "uniform_64k_direct": ("uniform", 1 << 16, "direct", 0.01, 0.0, 1e-3),
     "plummer_4k_direct": ("plummer", 1 << 12, "direct", 0.01, 0.0, 1e-3),
-    "plummer_1m_bh": ("plummer", 1 << 20, "bh", 0.01, 0.25, 1e-3),
+    # Barnes-Hut: theta in the REFERENCE convention (half-width / distance); conventional opening angle = 2 * theta
+    "plummer_1m_bh": ("plummer", 1 << 20, "bh", 0.01, 0.25, 1e-3),            # BASELINE configs[3]: theta_conv = 0.5
+    "two_galaxies_16m_bh": ("two_galaxies", 1 << 24, "bh", 0.01, 0.35, 1e-3),  # BASELINE configs[4]: theta_conv = 0.7
+    "two_galaxies_2m_bh": ("two_galaxies", 1 << 21, "bh", 0.01, 0.35, 1e-3),
 }
 
 
@@ -286,7 +289,7 @@ def run_ours(args, wl):
     sim.SetParticlesRaw(aos_in.data_ptr(), n, 40); sim.Tick(); sim.GetParticlesRaw(aos_out.data_ptr(), n, 40)  # warm
     barrier()
     e0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(e2e_steps):
         sim.SetParticlesRaw(aos_in.data_ptr(), n, 40)     # H2D: this rank's FParticle records
         sim.Tick()                                        # OctreeSearch.cpp:21-34
@@ -349,6 +352,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="plummer_1m_direct", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -71,7 +71,10 @@ typedef struct nbody_config {
                              is accepted when half-width / distance(group box, cell COM) < theta - never accepts what the
                              reference's per-body test would open); 1 = per body, exactly OctreeSearch.h:100-107 incl. the
                              visiting order (parity mode, slower) */
-  int32_t reserved[4];
+  int32_t group_size;     /* Barnes-Hut (mac = 0): bodies per walk group, 32 / 64 / 128 (default 64) */
+  int32_t group_pack;     /* Barnes-Hut (mac = 0): tree cells of <= group_pack * group_size bodies are cut into equal walk
+                             groups (default 2; larger = fuller lanes, looser group boxes) */
+  int32_t reserved[2];
   uint8_t nccl_unique_id[128]; /* multi-GPU: the ncclUniqueId from nbody_comm_unique_id on rank 0. All zeros with world > 1 =
                                   an EMULATED rank: no communicator; the handle evaluates its slice of the bodies given by
                                   nbody_set_bodies and never exchanges (several ranks can then be checked on one GPU) */
@@ -97,6 +100,8 @@ typedef struct nbody_stats {
   int32_t jsplit, i_per_thread, tree_nodes, tree_depth;
   float root_com[3];       /* BH: root centre of mass of the last build (the next reference-mode root origin) */
   float root_mass;
+  int32_t walk_groups;     /* BH: groups of the last build */
+  int32_t reserved0;
 } nbody_stats;
 
 typedef struct nbody_sim nbody_sim; /* opaque handle: owns device buffers, stream, events, NCCL communicator */
@@ -162,7 +167,7 @@ int nbody_get_local_ids(nbody_sim* sim, int64_t* ids, int64_t cap, int64_t* n_lo
 typedef enum nbody_param {
   NBODY_PARAM_G = 0, NBODY_PARAM_EPS = 1, NBODY_PARAM_THETA = 2, NBODY_PARAM_PH_DELTA_TIME = 3,
   NBODY_PARAM_METHOD = 4, NBODY_PARAM_LEAF_SIZE = 5, NBODY_PARAM_REFERENCE_ROOT = 6, NBODY_PARAM_SHOW_OCTREE = 7,
-  NBODY_PARAM_INITIALIZED = 8 /* read-only */, NBODY_PARAM_MAC = 9
+  NBODY_PARAM_INITIALIZED = 8 /* read-only */, NBODY_PARAM_MAC = 9, NBODY_PARAM_GROUP_SIZE = 10, NBODY_PARAM_GROUP_PACK = 11
 } nbody_param;
 int nbody_set_param(nbody_sim* sim, int32_t which, double value);
 int nbody_get_param(nbody_sim* sim, int32_t which, double* value);

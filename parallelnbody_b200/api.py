@@ -23,7 +23,7 @@ METHOD_DIRECT = 0
 METHOD_BARNES_HUT = 1
 
 PARAM_G, PARAM_EPS, PARAM_THETA, PARAM_PH_DELTA_TIME, PARAM_METHOD, PARAM_LEAF_SIZE, PARAM_REFERENCE_ROOT, \
-    PARAM_SHOW_OCTREE, PARAM_INITIALIZED, PARAM_MAC = range(10)
+    PARAM_SHOW_OCTREE, PARAM_INITIALIZED, PARAM_MAC, PARAM_GROUP_SIZE, PARAM_GROUP_PACK = range(12)
 
 # FParticle, OctreeSearch.h:9-18 (40 bytes)
 PARTICLE_DTYPE = np.dtype([("Mass", "<f4"), ("Position", "<f4", 3), ("Velocity", "<f4", 3), ("Acceleration", "<f4", 3)])
@@ -39,7 +39,7 @@ class _Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("method", C.c_int32), ("G", C.c_float), ("eps", C.c_float),
                 ("theta", C.c_float), ("ph_delta_time", C.c_float), ("device", C.c_int32), ("rank", C.c_int32),
                 ("world", C.c_int32), ("leaf_size", C.c_int32), ("reference_root", C.c_int32),
-                ("mac", C.c_int32), ("reserved", C.c_int32 * 4), ("nccl_unique_id", C.c_uint8 * 128), ("stream", C.c_void_p)]
+                ("mac", C.c_int32), ("group_size", C.c_int32), ("group_pack", C.c_int32), ("reserved", C.c_int32 * 2), ("nccl_unique_id", C.c_uint8 * 128), ("stream", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -48,7 +48,7 @@ class Stats(C.Structure):
                 ("ms_last_call", C.c_float), ("ms_force", C.c_float), ("ms_build", C.c_float),
                 ("ms_integrate", C.c_float), ("ms_comm", C.c_float), ("cube_size", C.c_float), ("jsplit", C.c_int32),
                 ("i_per_thread", C.c_int32), ("tree_nodes", C.c_int32), ("tree_depth", C.c_int32),
-                ("root_com", C.c_float * 3), ("root_mass", C.c_float)]
+                ("root_com", C.c_float * 3), ("root_mass", C.c_float), ("walk_groups", C.c_int32), ("reserved0", C.c_int32)]
 
     def as_dict(self):
         d = {}
@@ -165,13 +165,13 @@ class OctreeSearch:
     def __init__(self, method: int = METHOD_BARNES_HUT, G: float = 1e4, eps: float = 0.0, theta: float = 1.0,
                  PhDeltaTime: float = 0.01, device: int = 0, rank: int = 0, world: int = 1,
                  nccl_unique_id: bytes | None = None, leaf_size: int = 16, reference_root: bool = False,
-                 mac: int = 0, stream: int | None = None):
+                 mac: int = 0, group_size: int = 64, group_pack: int = 2, stream: int | None = None):
         self._L = load_library()
         cfg = _Config()
         _check(self._L.nbody_config_default(C.byref(cfg)))
         cfg.method, cfg.G, cfg.eps, cfg.theta, cfg.ph_delta_time = method, G, eps, theta, PhDeltaTime
         cfg.device, cfg.rank, cfg.world, cfg.leaf_size, cfg.reference_root = device, rank, world, leaf_size, int(reference_root)
-        cfg.mac = mac
+        cfg.mac, cfg.group_size, cfg.group_pack = mac, group_size, group_pack
         if world > 1:
             if nccl_unique_id is None or len(nccl_unique_id) != 128:
                 raise NBodyError(-1, "world > 1 needs the 128-byte nccl_unique_id broadcast from rank 0 "
@@ -348,6 +348,8 @@ class OctreeSearch:
     G = property(lambda s: s._getp(PARAM_G), lambda s, v: s._setp(PARAM_G, v))
     Initialized = property(lambda s: bool(s._getp(PARAM_INITIALIZED)))
     Mac = property(lambda s: int(s._getp(PARAM_MAC)), lambda s, v: s._setp(PARAM_MAC, v))
+    GroupSize = property(lambda s: int(s._getp(PARAM_GROUP_SIZE)), lambda s, v: s._setp(PARAM_GROUP_SIZE, v))
+    GroupPack = property(lambda s: int(s._getp(PARAM_GROUP_PACK)), lambda s, v: s._setp(PARAM_GROUP_PACK, v))
     LeafSize = property(lambda s: int(s._getp(PARAM_LEAF_SIZE)), lambda s, v: s._setp(PARAM_LEAF_SIZE, v))
 
     @property

@@ -26,7 +26,7 @@ namespace {
 constexpr int kMaxLevel = 21;            // 3 * 21 = 63 key bits
 constexpr int kLeafFlag = 1 << 8;
 constexpr int kBodyFlag = 1 << 30;       // walk-stack entry is a body index, not a node
-constexpr int kGroupBodies = 64;         // bodies per walk group (2 per lane)
+// walk groups hold <= group_size bodies (32 * B, B bodies per lane, B in {1, 2, 4})
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
 constexpr int kStackCap = 8192;          // per-warp walk stack entries (HBM/L2 resident)
@@ -47,13 +47,14 @@ struct Impl {
   int4* node_meta = nullptr;
   int2* node_range = nullptr;
   uint32_t* node_ready = nullptr;
-  int2* groups = nullptr;            // walk groups: body ranges of <= kGroupBodies neighbours
+  int2* groups = nullptr;            // walk groups: body ranges of <= group_size neighbours
   Counters* counters = nullptr;
   float4* root = nullptr;          // [0] = cube (centre, half-width); [1] = previous root COM (xyz) + valid flag (w)
   int* stacks = nullptr;
   int64_t cap_stacks = 0;
   float* boxes = nullptr; int64_t cap_boxes = 0;
   int n = 0;
+  int built_group_size = 0;
 };
 
 Impl* impl_of(BHState& st) {
@@ -133,8 +134,12 @@ __device__ __forceinline__ uint32_t compact21(uint64_t x) {
   x = (x | x >> 32) & 0x1fffffull;
   return (uint32_t)x;
 }
-__device__ __forceinline__ uint32_t quantize(float x, float lo, float scale) {
-  const float f = floorf((x - lo) * scale);
+// Cell index along one axis: u = (x - centre) / half in [-1, 1) -> floor((u + 1) * 2^20), clamped. The division keeps the
+// reference's octant comparisons exact where they are exact: x >= centre <=> the top bit is set (OctreeSearch.h:50-56),
+// e.g. for the central body that CreateSpacePoints puts exactly at the root centre (OctreeSearch.cpp:68-70).
+__device__ __forceinline__ uint32_t quantize(float x, float centre, float half) {
+  const float u = __fdiv_rn(__fsub_rn(x, centre), half);
+  const float f = floorf(__fmul_rn(__fadd_rn(u, 1.f), 1048576.f));
   return (uint32_t)fminf(fmaxf(f, 0.f), 2097151.f);
 }
 
@@ -143,9 +148,8 @@ morton_kernel(const float4* __restrict__ posm, const int n, const float4* __rest
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 c = root[0];
-  const float scale = 1048576.f / c.w;  // 2^21 cells across the full width 2 * half
   const float4 p = ld_stream(posm + i);
-  const uint32_t qx = quantize(p.x, c.x - c.w, scale), qy = quantize(p.y, c.y - c.w, scale), qz = quantize(p.z, c.z - c.w, scale);
+  const uint32_t qx = quantize(p.x, c.x, c.w), qy = quantize(p.y, c.y, c.w), qz = quantize(p.z, c.z, c.w);
   keys[i] = expand21(qx) << 2 | expand21(qy) << 1 | expand21(qz);   // octant digit = 4*X + 2*Y + Z (OctreeSearch.h:50-56)
 }
 
@@ -169,7 +173,18 @@ __device__ __forceinline__ int common_levels(uint64_t a, uint64_t b) {
   return (__clzll((long long)x) - 1) / 3;
 }
 
-__global__ void tree_init_kernel(const uint64_t* __restrict__ keys, const int n, int2* __restrict__ range,
+// Cuts the body range [b, e) into ceil(len / group_size) near-equal walk groups.
+__device__ __forceinline__ void emit_groups(const int b, const int e, const int group_size, int2* __restrict__ groups,
+                                            Counters* __restrict__ c) {
+  const int len = e - b;
+  if (len <= 0) return;
+  const int chunks = (len + group_size - 1) / group_size;
+  const int g0 = atomicAdd(&c->ngroups, chunks);
+  for (int k = 0; k < chunks; k++)
+    groups[g0 + k] = make_int2(b + (int)((long long)len * k / chunks), b + (int)((long long)len * (k + 1) / chunks));
+}
+
+__global__ void tree_init_kernel(const uint64_t* __restrict__ keys, const int n, const int group_size, const int super, int2* __restrict__ range,
                                  int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
                                  Counters* __restrict__ c) {
   const int lvl = n > 1 ? common_levels(keys[0], keys[n - 1]) : kMaxLevel;
@@ -180,14 +195,15 @@ __global__ void tree_init_kernel(const uint64_t* __restrict__ keys, const int n,
   for (int k = 0; k < kMaxLevel + 4; k++) c->gen_off[k] = 1;
   c->gen_off[0] = 0;
   c->interactions = 0;
-  if (n <= kGroupBodies) { groups[0] = make_int2(0, n); c->ngroups = 1; }
+  if (n <= super) emit_groups(0, n, group_size, groups, c);
 }
 
 // One generation of the top-down split: every node created by the previous generation either becomes a leaf or is cut
 // at its level's octant digit into its non-empty children (8 lanes per node, one octant boundary each, found by
 // binary search in the sorted keys). Equivalent of the recursive re-insertion in Octree::Add (OctreeSearch.h:65-78).
 __global__ void __launch_bounds__(256)
-tree_split_kernel(const int gen, const uint64_t* __restrict__ keys, const int leaf_size, int2* __restrict__ range,
+tree_split_kernel(const int gen, const uint64_t* __restrict__ keys, const int leaf_size, const int group_size, const int super,
+                  int2* __restrict__ range,
                   int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
                   Counters* __restrict__ c) {
   const int gb = c->gen_off[gen], ge = c->gen_off[gen + 1];
@@ -202,12 +218,8 @@ tree_split_kernel(const int gen, const uint64_t* __restrict__ keys, const int le
     if (cnt <= leaf_size || level >= kMaxLevel) {
       if (sub == 0) {
         meta[node] = make_int4(r.x, cnt, level | kLeafFlag, m.w);
-        // > kGroupBodies bodies in one deepest-level cell (coincident to 2^-21 of the cube): walk them in chunks
-        if (cnt > kGroupBodies) {
-          const int chunks = (cnt + kGroupBodies - 1) / kGroupBodies;
-          const int g0 = atomicAdd(&c->ngroups, chunks);
-          for (int k = 0; k < chunks; k++) groups[g0 + k] = make_int2(r.x + k * kGroupBodies, min(r.y, r.x + (k + 1) * kGroupBodies));
-        }
+        // > super bodies in one deepest-level cell (coincident to 2^-21 of the cube): walk them in chunks
+        if (cnt > super) emit_groups(r.x, r.y, group_size, groups, c);
       }
       maxlvl = max(maxlvl, m.w >= 0 ? (meta[m.w].z & 255) + 1 : 0);   // depth of the leaf's cell in the reference's tree
       continue;
@@ -232,7 +244,19 @@ tree_split_kernel(const int gen, const uint64_t* __restrict__ keys, const int le
       range[child] = make_int2(start, next);
       meta[child] = make_int4(0, 0, cc > 1 ? common_levels(keys[start], keys[next - 1]) : kMaxLevel, node);
       ready[child] = 0;
-      if (cc <= kGroupBodies && cnt > kGroupBodies) groups[atomicAdd(&c->ngroups, 1)] = make_int2(start, next);
+    }
+    // Walk groups. A cell with more than `super` bodies hands its small children (<= super bodies each) to the walk:
+    // runs of consecutive small children (adjacent octants, contiguous bodies) are cut into equal chunks of <= group_size
+    // bodies, so the walk's lanes are well filled while every chunk stays inside this cell.
+    if (cnt > super) {
+      int run_begin = 0, run_end = 0;
+      for (int k = 0; k < 8; k++) {
+        const int ck = __shfl_sync(gmask, cc, gshift + k), sk = __shfl_sync(gmask, start, gshift + k);
+        if (sub != 0 || ck == 0) continue;
+        if (ck <= super) { if (run_end == run_begin) run_begin = sk; run_end = sk + ck; }
+        else { emit_groups(run_begin, run_end, group_size, groups, c); run_begin = run_end = 0; }
+      }
+      if (sub == 0) emit_groups(run_begin, run_end, group_size, groups, c);
     }
     if (sub == 0) meta[node] = make_int4(base, nchild, level, m.w);
   }
@@ -300,31 +324,40 @@ monopole_kernel(const float4* __restrict__ posm, const int2* __restrict__ range,
 // and the bodies of opened leaves are appended to a 64-entry ring in shared memory; whenever 32 are pending, all lanes
 // evaluate them against their bodies with the direct-sum interaction (FP32-pipe bound, no divergence). Opened cells
 // push their children. The stack lives in a per-warp slab of global memory (L2 resident, coalesced).
-template <bool EPS0>
-__device__ __forceinline__ void eval_list(const float4* __restrict__ ring, const int head,
-                                          const float (&px)[2], const float (&py)[2], const float (&pz)[2], const float eps2,
-                                          float (&ax)[2], float (&ay)[2], float (&az)[2]) {
-#pragma unroll 8
-  for (int j = 0; j < 32; j++) {
-    const float4 s = ring[(head + j) & (kListCap - 1)];
-    interact<EPS0>(s, px[0], py[0], pz[0], eps2, ax[0], ay[0], az[0]);
-    interact<EPS0>(s, px[1], py[1], pz[1], eps2, ax[1], ay[1], az[1]);
+// The pending ring is SoA (x[64] | y[64] | z[64] | m[64]) so that one LDS.128 yields four consecutive x (y, z, m) and the
+// evaluation runs on PAIRS of entries with Blackwell packed fp32 (FADD2 / FFMA2 / FMUL2), as K1 does.
+template <int B, bool EPS0>
+__device__ __forceinline__ void eval_list(const float* __restrict__ ring, const int head, const float2 (&nx)[B],
+                                          const float2 (&ny)[B], const float2 (&nz)[B], const float2 eps2,
+                                          float2 (&ax)[B], float2 (&ay)[B], float2 (&az)[B]) {
+#pragma unroll 2
+  for (int j = 0; j < 32; j += 4) {
+    const float4 X = *reinterpret_cast<const float4*>(ring + head + j);
+    const float4 Y = *reinterpret_cast<const float4*>(ring + kListCap + head + j);
+    const float4 Z = *reinterpret_cast<const float4*>(ring + 2 * kListCap + head + j);
+    const float4 M = *reinterpret_cast<const float4*>(ring + 3 * kListCap + head + j);
+#pragma unroll
+    for (int k = 0; k < B; k++) {
+      interact2<EPS0>(f2(X.x, X.y), f2(Y.x, Y.y), f2(Z.x, Z.y), f2(M.x, M.y), nx[k], ny[k], nz[k], eps2, ax[k], ay[k], az[k]);
+      interact2<EPS0>(f2(X.z, X.w), f2(Y.z, Y.w), f2(Z.z, Z.w), f2(M.z, M.w), nx[k], ny[k], nz[k], eps2, ax[k], ay[k], az[k]);
+    }
   }
 }
 
-template <bool EPS0>
+template <int B, bool EPS0>
 __global__ void __launch_bounds__(kWalkThreads)
 bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com, const int4* __restrict__ node_meta,
                      const int2* __restrict__ groups, Counters* __restrict__ c,
                      const float4* __restrict__ root, const float theta2, const float eps2, const float G, const int t0,
                      const int t1, int* __restrict__ stacks, float4* __restrict__ acc) {
-  __shared__ float4 ring_all[kWalkWarps][kListCap];
+  __shared__ __align__(16) float ring_all[kWalkWarps][4 * kListCap];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float4* ring = ring_all[w];
+  float* ring = ring_all[w];
   int* stack = stacks + (size_t)(blockIdx.x * kWalkWarps + w) * kStackCap;
   const int ngroups = c->ngroups;
   const float root_half = root[0].w;
   const unsigned lt = (1u << lane) - 1u;
+  const float2 eps2v = f2(eps2, eps2);
   unsigned long long inter = 0;
   while (true) {
     int g = 0;
@@ -334,13 +367,14 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
     const int2 r = groups[g];
     const int ntarget = min(r.y, t1) - max(r.x, t0);
     if (ntarget <= 0) continue;
-    float px[2], py[2], pz[2], ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f}, az[2] = {0.f, 0.f};
+    float2 nx[B], ny[B], nz[B], ax[B], ay[B], az[B];   // negated target coordinates / accumulators, duplicated per half
     float lox = 3.4e38f, loy = 3.4e38f, loz = 3.4e38f, hix = -3.4e38f, hiy = -3.4e38f, hiz = -3.4e38f;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < B; k++) {
+      ax[k] = f2(0.f, 0.f); ay[k] = f2(0.f, 0.f); az[k] = f2(0.f, 0.f);
       const int i = r.x + lane + 32 * k;
       const float4 p = posm[i < r.y ? i : r.x];
-      px[k] = p.x; py[k] = p.y; pz[k] = p.z;
+      nx[k] = f2(-p.x, -p.x); ny[k] = f2(-p.y, -p.y); nz[k] = f2(-p.z, -p.z);
       lox = fminf(lox, p.x); loy = fminf(loy, p.y); loz = fminf(loz, p.z);
       hix = fmaxf(hix, p.x); hiy = fmaxf(hiy, p.y); hiz = fmaxf(hiz, p.z);
     }
@@ -391,11 +425,14 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
       top += total;
       // accepted cells / bodies join the pending interaction ring
       const unsigned mask = __ballot_sync(0xffffffffu, has_item);
-      if (has_item) ring[(head + pending + __popc(mask & lt)) & (kListCap - 1)] = item;
+      if (has_item) {
+        const int slot = (head + pending + __popc(mask & lt)) & (kListCap - 1);
+        ring[slot] = item.x; ring[kListCap + slot] = item.y; ring[2 * kListCap + slot] = item.z; ring[3 * kListCap + slot] = item.w;
+      }
       pending += __popc(mask);
       __syncwarp();
       if (pending >= 32) {
-        eval_list<EPS0>(ring, head, px, py, pz, eps2, ax, ay, az);
+        eval_list<B, EPS0>(ring, head, nx, ny, nz, eps2v, ax, ay, az);
         head = (head + 32) & (kListCap - 1);
         pending -= 32;
         entries += 32;
@@ -403,17 +440,20 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
       }
     }
     if (pending > 0) {  // tail: pad the ring with massless entries so the evaluation stays branch-free
-      if (lane >= pending) ring[(head + lane) & (kListCap - 1)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane >= pending) {
+        const int slot = (head + lane) & (kListCap - 1);
+        ring[slot] = 0.f; ring[kListCap + slot] = 0.f; ring[2 * kListCap + slot] = 0.f; ring[3 * kListCap + slot] = 0.f;
+      }
       __syncwarp();
-      eval_list<EPS0>(ring, head, px, py, pz, eps2, ax, ay, az);
+      eval_list<B, EPS0>(ring, head, nx, ny, nz, eps2v, ax, ay, az);
       entries += pending;
       __syncwarp();
     }
     inter += entries * (unsigned long long)ntarget;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < B; k++) {
       const int i = r.x + lane + 32 * k;
-      if (i < r.y && i >= t0 && i < t1) acc[i] = make_float4(G * ax[k], G * ay[k], G * az[k], 0.f);
+      if (i < r.y && i >= t0 && i < t1) acc[i] = make_float4(G * (ax[k].x + ax[k].y), G * (ay[k].x + ay[k].y), G * (az[k].x + az[k].y), 0.f);
     }
   }
   if (lane == 0 && inter) atomicAdd(&c->interactions, inter);
@@ -508,12 +548,20 @@ __global__ void iota_kernel(int32_t* ids, int n, int first) {
   if (i < n) ids[i] = first + i;
 }
 
-int walk_grid(bool eps0) {
+template <int B, bool EPS0>
+int launch_walk(Impl* m, const BHParams& p, const float4* posm, float4* acc, int t0, int t1, cudaStream_t s) {
   int per_sm = 0;
-  if (eps0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<true>, kWalkThreads, 0);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<false>, kWalkThreads, 0);
-  per_sm = std::max(1, std::min(per_sm, 8));
-  return kNumSMsB200 * per_sm;
+  NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<B, EPS0>, kWalkThreads, 0));
+  const int grid = kNumSMsB200 * std::max(1, std::min(per_sm, 8));
+  const int64_t need = (int64_t)grid * kWalkWarps * kStackCap;
+  if (need > m->cap_stacks) {
+    NB_CUDA(cudaStreamSynchronize(s));
+    NB_TRY(realloc_dev(&m->stacks, (size_t)need));
+    m->cap_stacks = need;
+  }
+  bh_walk_group_kernel<B, EPS0><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, m->groups, m->counters, m->root,
+                                                              p.theta * p.theta, p.eps2, p.G, t0, t1, m->stacks, acc);
+  return 0;
 }
 
 }  // namespace
@@ -558,11 +606,14 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
   m->sorted = radix_sort_pairs(m->sort, n, 3 * kMaxLevel, s, launches);
   gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[m->sorted], n, posm_in, vel_in, ids_in, posm, vel, ids);
   const uint64_t* keys = m->sort.keys[m->sorted];
-  tree_init_kernel<<<1, 1, 0, s>>>(keys, n, m->node_range, m->node_meta, m->node_ready, m->groups, m->counters);
+  if (p.group_size != 32 && p.group_size != 64 && p.group_size != 128) { set_error("Barnes-Hut: group_size must be 32, 64 or 128"); return -1; }
+  m->built_group_size = p.group_size;
+  const int super = p.group_size * std::max(1, p.group_pack);
+  tree_init_kernel<<<1, 1, 0, s>>>(keys, n, p.group_size, super, m->node_range, m->node_meta, m->node_ready, m->groups, m->counters);
   *launches += 2;
   const int grid = kNumSMsB200 * 4;
   for (int gen = 0; gen <= kMaxLevel; gen++)
-    tree_split_kernel<<<grid, 256, 0, s>>>(gen, keys, std::max(1, p.leaf_size), m->node_range, m->node_meta, m->node_ready,
+    tree_split_kernel<<<grid, 256, 0, s>>>(gen, keys, std::max(1, p.leaf_size), p.group_size, super, m->node_range, m->node_meta, m->node_ready,
                                            m->groups, m->counters);
   monopole_kernel<<<grid, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
   *launches += kMaxLevel + 2;
@@ -580,20 +631,14 @@ int bh_forces(BHState& st, const BHParams& p, const float4* posm, float4* acc, i
     bh_walk_body_kernel<<<(unsigned)ceil_div(t1 - t0, 128), 128, 0, s>>>(posm, m->node_com, m->node_meta, m->counters, m->root,
                                                                           p.theta, p.eps2, p.G, t0, t1, acc);
   } else {
-    const int grid = walk_grid(eps0);
-    const int64_t need = (int64_t)grid * kWalkWarps * kStackCap;
-    if (need > m->cap_stacks) {
-      NB_CUDA(cudaStreamSynchronize(s));
-      NB_TRY(realloc_dev(&m->stacks, (size_t)need));
-      m->cap_stacks = need;
-    }
-    const float theta2 = p.theta * p.theta;
-    if (eps0)
-      bh_walk_group_kernel<true><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, m->groups,
-                                                               m->counters, m->root, theta2, p.eps2, p.G, t0, t1, m->stacks, acc);
-    else
-      bh_walk_group_kernel<false><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, m->groups,
-                                                                m->counters, m->root, theta2, p.eps2, p.G, t0, t1, m->stacks, acc);
+    if (m->built_group_size != p.group_size) { set_error("Barnes-Hut: group_size changed since the tree was built"); return -5; }
+    const int B = p.group_size / 32;
+    int rc = 0;
+    if (eps0) rc = B == 1 ? launch_walk<1, true>(m, p, posm, acc, t0, t1, s) : B == 2 ? launch_walk<2, true>(m, p, posm, acc, t0, t1, s)
+                                                                                      : launch_walk<4, true>(m, p, posm, acc, t0, t1, s);
+    else rc = B == 1 ? launch_walk<1, false>(m, p, posm, acc, t0, t1, s) : B == 2 ? launch_walk<2, false>(m, p, posm, acc, t0, t1, s)
+                                                                                   : launch_walk<4, false>(m, p, posm, acc, t0, t1, s);
+    NB_TRY(rc);
   }
   *launches += 1;
   NB_CUDA(cudaGetLastError());

@@ -22,6 +22,8 @@ struct BHParams {
   int leaf_size = 16;
   bool reference_root = false;
   int mac = kMacGroup;
+  int group_size = 64;  // bodies per walk group: 32, 64 or 128 (1, 2 or 4 per lane)
+  int group_pack = 2;   // cells of <= group_pack * group_size bodies are cut into equal walk groups
 };
 
 struct BHState {

@@ -272,6 +272,8 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
     bp.G = s->cfg.G; bp.eps2 = s->cfg.eps * s->cfg.eps; bp.theta = s->cfg.theta;
     bp.leaf_size = std::max(1, s->cfg.leaf_size); bp.reference_root = s->cfg.reference_root != 0;
     bp.mac = s->cfg.mac;
+    bp.group_size = s->cfg.group_size;
+    bp.group_pack = s->cfg.group_pack;
     double launches = 0;
     // Morton reordering of ALL bodies (identical on every rank: same data, stable sort), tree + monopoles
     NB_TRY(bh_build(s->tree, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_global, s->d_box,
@@ -395,6 +397,8 @@ int nbody_config_default(nbody_config* cfg) {
   cfg->leaf_size = 16;
   cfg->reference_root = 0;
   cfg->mac = 0;
+  cfg->group_size = 64;
+  cfg->group_pack = 2;
   return NBODY_OK;
 }
 
@@ -411,6 +415,9 @@ int nbody_create(nbody_sim** out, const nbody_config* cfg) {
   if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return invalid("bad rank/world");
   if (!(cfg->eps >= 0.f) || !(cfg->theta >= 0.f)) return invalid("eps and theta must be >= 0");
   if (cfg->mac != 0 && cfg->mac != 1) return invalid("mac must be 0 (group) or 1 (per body, reference rule)");
+  if (cfg->group_size != 32 && cfg->group_size != 64 && cfg->group_size != 128) return invalid("group_size must be 32, 64 or 128");
+  if (cfg->leaf_size < 1 || cfg->leaf_size > 64) return invalid("leaf_size must be in [1, 64]");
+  if (cfg->group_pack < 1 || cfg->group_pack > 64) return invalid("group_pack must be in [1, 64]");
   NB_TRY(check_device(cfg->device));
   nbody_sim* s = new nbody_sim();
   s->cfg = *cfg;
@@ -626,6 +633,8 @@ int nbody_set_param(nbody_sim* s, int32_t which, double v) {
     case NBODY_PARAM_REFERENCE_ROOT: s->cfg.reference_root = v != 0; return NBODY_OK;
     case NBODY_PARAM_SHOW_OCTREE: s->show_octree = v != 0; return NBODY_OK;
     case NBODY_PARAM_MAC: if (v != 0 && v != 1) return invalid("mac must be 0 or 1"); s->cfg.mac = (int)v; return NBODY_OK;
+    case NBODY_PARAM_GROUP_SIZE: if (v != 32 && v != 64 && v != 128) return invalid("group_size must be 32, 64 or 128"); s->cfg.group_size = (int)v; return NBODY_OK;
+    case NBODY_PARAM_GROUP_PACK: if (v < 1 || v > 64) return invalid("group_pack must be in [1, 64]"); s->cfg.group_pack = (int)v; return NBODY_OK;
     case NBODY_PARAM_METHOD: return invalid("method is fixed at nbody_create (device layout depends on it)");
     default: return invalid("unknown or read-only parameter");
   }
@@ -644,6 +653,8 @@ int nbody_get_param(nbody_sim* s, int32_t which, double* v) {
     case NBODY_PARAM_SHOW_OCTREE: *v = s->show_octree; return NBODY_OK;
     case NBODY_PARAM_INITIALIZED: *v = s->initialized; return NBODY_OK;
     case NBODY_PARAM_MAC: *v = s->cfg.mac; return NBODY_OK;
+    case NBODY_PARAM_GROUP_SIZE: *v = s->cfg.group_size; return NBODY_OK;
+    case NBODY_PARAM_GROUP_PACK: *v = s->cfg.group_pack; return NBODY_OK;
     default: return invalid("unknown parameter");
   }
 }
@@ -680,7 +691,7 @@ int nbody_stats_get(nbody_sim* s, nbody_stats* out) {
   out->ms_integrate = s->ms_integrate; out->ms_comm = s->ms_comm;
   out->cube_size = s->cube_size;
   out->jsplit = s->plan.jsplit; out->i_per_thread = s->plan.i_per_thread;
-  out->tree_nodes = s->tree.n_nodes_host; out->tree_depth = s->tree.depth_host;
+  out->tree_nodes = s->tree.n_nodes_host; out->tree_depth = s->tree.depth_host; out->walk_groups = s->tree.n_groups_host;
   memcpy(out->root_com, s->tree.root_com_host, sizeof(out->root_com));
   out->root_mass = s->tree.root_mass_host;
   return NBODY_OK;

@@ -52,8 +52,8 @@ def test_radix_sort_partial_bits_and_presorted():
 # ---------------------------------------------------------------------------------------------- K4 + K6 + K7 tree
 def _morton_host(posm, cube):
     c, half = np.asarray(cube[:3], np.float32), np.float32(cube[3])
-    scale = np.float32(1048576.0) / half
-    q = np.floor((posm[:, :3] - (c - half)) * scale)
+    u = (posm[:, :3].astype(np.float32) - c) / half                      # fp32, as the kernel
+    q = np.floor((u + np.float32(1.0)) * np.float32(1048576.0))
     q = np.clip(q, 0, 2097151).astype(np.uint64)
 
     def expand(v):

@@ -5,18 +5,22 @@ import numpy as np
 import parallelnbody_b200 as P
 from parallelnbody_b200 import ic
 
-for n in (1 << 16, 1 << 20, 1 << 22):
+sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1 << 20, 1 << 22]
+for n in sizes:
     posm, vel = ic.plummer(n, seed=1234)
     keys = np.random.default_rng(1).integers(0, 1 << 63, n, dtype=np.uint64)
     _, _, ms = P.sort_pairs_u64(keys, 63, timed=True)
     print(f"N={n}: radix sort 63-bit pairs {ms:.3f} ms = {n / ms * 1e-6:.2f} Gkeys/s")
-    for th in (0.25, 0.35, 0.5):
-        for leaf in (8, 16, 32):
-            with P.OctreeSearch(method=P.METHOD_BARNES_HUT, eps=0.01, theta=th, leaf_size=leaf) as s:
-                s.SetBodies(posm, vel)
-                s.Step(1e-3, 2)
-                s.Step(1e-3, 5)
-                st = s.Stats()
-                print(f"N={n} theta={th} leaf={leaf}: {st['ms_last_call'] / 5:.3f} ms/step  build {st['ms_build'] / 5:.3f}  walk {st['ms_force'] / 5:.3f}  "
-                      f"integ {st['ms_integrate'] / 5:.3f}  nodes {st['tree_nodes']} depth {st['tree_depth']}  inter/body {st['interactions'] / n:.0f}  "
-                      f"{st['interactions'] / (st['ms_force'] / 5 * 1e-3):.3e} inter/s", flush=True)
+    for th in (0.25, 0.35):
+        for gs in (64, 128):
+            for pack in (1, 2, 4, 8, 16):
+                leaf = 16
+                with P.OctreeSearch(method=P.METHOD_BARNES_HUT, eps=0.01, theta=th, leaf_size=leaf, group_size=gs, group_pack=pack) as s:
+                    s.SetBodies(posm, vel)
+                    s.Step(1e-3, 2)
+                    s.Step(1e-3, 5)
+                    st = s.Stats()
+                    fill = n / max(1, st['walk_groups']) / gs
+                    print(f"N={n} theta={th} group={gs} pack={pack} leaf={leaf}: {st['ms_last_call'] / 5:.3f} ms/step  build {st['ms_build'] / 5:.3f}  walk {st['ms_force'] / 5:.3f}  "
+                          f"nodes {st['tree_nodes']} depth {st['tree_depth']} groups {st['walk_groups']} fill {fill:.2f}  inter/body {st['interactions'] / n:.0f}  "
+                          f"{st['interactions'] / (st['ms_force'] / 5 * 1e-3):.3e} inter/s", flush=True)
