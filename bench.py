@@ -166,7 +166,11 @@ def workload_config(args, wl, world):
     return {"workload": f"{icname} N={n} {'softened direct sum' if method == 'direct' else 'Barnes-Hut'} + kick-drift",
             "name": args.workload, "N": n, "eps": eps, "dt": dt, "G": 1e4, "method": method,
             "theta_reference_convention": theta if method == "bh" else 0.0,
-            "partition": f"i-rows over {world} GPU(s), NCCL all-gather of float4 positions per step" if world > 1 else "1 GPU",
+            "partition": ("1 GPU" if world == 1 else
+                          f"i-rows over {world} GPUs, NCCL all-gather of float4 positions per step" if method == "direct" else
+                          f"Morton domain split over {world} GPUs, body migration + locally-essential-tree exchange (NCCL all-to-all-v)"
+                          if getattr(args, "bh_exchange", 0) == 0 else
+                          f"replicated tree, Morton-order slices over {world} GPUs, all-gather of positions + velocities"),
             "l2": "flushed between timed steps (256 MiB memset); sources (16 B/body) are re-read from L2 by design",
             "seed": 1234}
 
@@ -245,7 +249,7 @@ def run_ours(args, wl):
     posm, vel = make_ic(icname, n)
     meth = P.METHOD_DIRECT if method == "direct" else P.METHOD_BARNES_HUT
     sim = P.OctreeSearch(method=meth, G=1e4, eps=eps, theta=theta if method == "bh" else 0.0, PhDeltaTime=dt,
-                         device=local_rank, rank=rank, world=world, nccl_unique_id=uid)
+                         device=local_rank, rank=rank, world=world, nccl_unique_id=uid, bh_exchange=args.bh_exchange)
     sim.SetBodies(posm, vel)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -353,6 +357,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="plummer_1m_direct", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--bh-exchange", type=int, default=0, choices=[0, 1],
+                    help="multi-GPU Barnes-Hut: 0 = Morton domain split + LET exchange, 1 = replicated tree")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -74,7 +74,10 @@ typedef struct nbody_config {
   int32_t group_size;     /* Barnes-Hut (mac = 0): bodies per walk group, 32 / 64 / 128 (default 64) */
   int32_t group_pack;     /* Barnes-Hut (mac = 0): tree cells of <= group_pack * group_size bodies are cut into equal walk
                              groups (default 2; larger = fuller lanes, looser group boxes) */
-  int32_t reserved[2];
+  int32_t bh_exchange;    /* multi-GPU Barnes-Hut: 0 = Morton domain split, body migration and locally-essential-tree exchange
+                             (each rank holds only its domain); 1 = replicated tree (every rank holds all bodies, walks its
+                             slice of the Morton order, all-gathers positions and velocities) */
+  int32_t reserved[1];
   uint8_t nccl_unique_id[128]; /* multi-GPU: the ncclUniqueId from nbody_comm_unique_id on rank 0. All zeros with world > 1 =
                                   an EMULATED rank: no communicator; the handle evaluates its slice of the bodies given by
                                   nbody_set_bodies and never exchanges (several ranks can then be checked on one GPU) */

@@ -39,7 +39,7 @@ class _Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("method", C.c_int32), ("G", C.c_float), ("eps", C.c_float),
                 ("theta", C.c_float), ("ph_delta_time", C.c_float), ("device", C.c_int32), ("rank", C.c_int32),
                 ("world", C.c_int32), ("leaf_size", C.c_int32), ("reference_root", C.c_int32),
-                ("mac", C.c_int32), ("group_size", C.c_int32), ("group_pack", C.c_int32), ("reserved", C.c_int32 * 2), ("nccl_unique_id", C.c_uint8 * 128), ("stream", C.c_void_p)]
+                ("mac", C.c_int32), ("group_size", C.c_int32), ("group_pack", C.c_int32), ("bh_exchange", C.c_int32), ("reserved", C.c_int32 * 1), ("nccl_unique_id", C.c_uint8 * 128), ("stream", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -165,13 +165,13 @@ class OctreeSearch:
     def __init__(self, method: int = METHOD_BARNES_HUT, G: float = 1e4, eps: float = 0.0, theta: float = 1.0,
                  PhDeltaTime: float = 0.01, device: int = 0, rank: int = 0, world: int = 1,
                  nccl_unique_id: bytes | None = None, leaf_size: int = 16, reference_root: bool = False,
-                 mac: int = 0, group_size: int = 64, group_pack: int = 2, stream: int | None = None):
+                 mac: int = 0, group_size: int = 64, group_pack: int = 2, bh_exchange: int = 0, stream: int | None = None):
         self._L = load_library()
         cfg = _Config()
         _check(self._L.nbody_config_default(C.byref(cfg)))
         cfg.method, cfg.G, cfg.eps, cfg.theta, cfg.ph_delta_time = method, G, eps, theta, PhDeltaTime
         cfg.device, cfg.rank, cfg.world, cfg.leaf_size, cfg.reference_root = device, rank, world, leaf_size, int(reference_root)
-        cfg.mac, cfg.group_size, cfg.group_pack = mac, group_size, group_pack
+        cfg.mac, cfg.group_size, cfg.group_pack, cfg.bh_exchange = mac, group_size, group_pack, bh_exchange
         if world > 1:
             if nccl_unique_id is None or len(nccl_unique_id) != 128:
                 raise NBodyError(-1, "world > 1 needs the 128-byte nccl_unique_id broadcast from rank 0 "

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "comm.h"
 #include "direct_kernels.cuh"
 #include "radix_sort.cuh"
 
@@ -31,6 +32,9 @@ constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
 constexpr int kStackCap = 8192;          // per-warp walk stack entries (HBM/L2 resident)
 constexpr int kListCap = 64;             // per-warp interaction ring in shared memory
+constexpr int kLetSamples = 256;         // key samples per rank for the domain splitters
+constexpr int kLetBoxes = 64;            // boxes describing a rank's domain to its peers
+constexpr int kMaxWorld = 16;
 
 struct Counters {
   int nnodes, ngroups, ticket, depth, next_group, overflow, pad0, pad1;
@@ -55,6 +59,23 @@ struct Impl {
   float* boxes = nullptr; int64_t cap_boxes = 0;
   int n = 0;
   int built_group_size = 0;
+  // --- multi-GPU domain decomposition + locally-essential-tree exchange (K9), allocated on first use
+  int let_world = 0;
+  uint64_t* samples = nullptr;     // [world * kLetSamples] gathered key samples
+  uint64_t* splitters = nullptr;   // [world - 1]
+  int* send_off = nullptr;         // [world + 1] body ranges per destination rank
+  int* all_off = nullptr;          // [world * (world + 1)] every rank's send_off / LET counts
+  float* peer_boxes = nullptr;     // [world * kLetBoxes * 6] (min xyz, max xyz) of each rank's body chunks
+  uint32_t* visit = nullptr;       // per node: which peers still descend through it
+  int64_t cap_visit = 0;
+  float4* let_out = nullptr;       // [world * cap_let] per-peer export lists
+  int* let_cnt = nullptr;          // [world]
+  int64_t cap_let = 0;
+  float4* let_in = nullptr;        // received points
+  float4* let_sorted = nullptr;    // the same in Morton order (sources of the LET tree)
+  int64_t cap_let_in = 0;
+  float4* all_pos = nullptr;       // diagnostics: every rank's bodies (energy)
+  int64_t cap_all_pos = 0;
 };
 
 Impl* impl_of(BHState& st) {
@@ -161,8 +182,8 @@ gather_bodies_kernel(const uint32_t* __restrict__ order, const int n, const floa
   if (i >= n) return;
   const uint32_t j = order[i];
   st_stream(posm_out + i, posm_in[j]);
-  st_stream(vel_out + i, vel_in[j]);
-  ids_out[i] = ids_in[j];
+  if (vel_in) st_stream(vel_out + i, vel_in[j]);
+  if (ids_in) ids_out[i] = ids_in[j];
 }
 
 // ---- K6: octree topology ------------------------------------------------------------------------------------
@@ -347,9 +368,11 @@ __device__ __forceinline__ void eval_list(const float* __restrict__ ring, const 
 template <int B, bool EPS0>
 __global__ void __launch_bounds__(kWalkThreads)
 bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com, const int4* __restrict__ node_meta,
-                     const int2* __restrict__ groups, Counters* __restrict__ c,
+                     const float4* __restrict__ tgt, const int2* __restrict__ groups, Counters* __restrict__ c,
                      const float4* __restrict__ root, const float theta2, const float eps2, const float G, const int t0,
-                     const int t1, int* __restrict__ stacks, float4* __restrict__ acc) {
+                     const int t1, const int accumulate, int* __restrict__ stacks, float4* __restrict__ acc) {
+  // posm / node_* = the SOURCE tree; tgt / groups / c = the targets and their walk groups (the same tree, or - for
+  // the locally-essential points received from other ranks - the local tree whose bodies are being accelerated)
   __shared__ __align__(16) float ring_all[kWalkWarps][4 * kListCap];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* ring = ring_all[w];
@@ -373,7 +396,7 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
     for (int k = 0; k < B; k++) {
       ax[k] = f2(0.f, 0.f); ay[k] = f2(0.f, 0.f); az[k] = f2(0.f, 0.f);
       const int i = r.x + lane + 32 * k;
-      const float4 p = posm[i < r.y ? i : r.x];
+      const float4 p = tgt[i < r.y ? i : r.x];
       nx[k] = f2(-p.x, -p.x); ny[k] = f2(-p.y, -p.y); nz[k] = f2(-p.z, -p.z);
       lox = fminf(lox, p.x); loy = fminf(loy, p.y); loz = fminf(loz, p.z);
       hix = fmaxf(hix, p.x); hiy = fmaxf(hiy, p.y); hiz = fmaxf(hiz, p.z);
@@ -453,7 +476,11 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
 #pragma unroll
     for (int k = 0; k < B; k++) {
       const int i = r.x + lane + 32 * k;
-      if (i < r.y && i >= t0 && i < t1) acc[i] = make_float4(G * (ax[k].x + ax[k].y), G * (ay[k].x + ay[k].y), G * (az[k].x + az[k].y), 0.f);
+      if (i < r.y && i >= t0 && i < t1) {
+        float4 a = make_float4(G * (ax[k].x + ax[k].y), G * (ay[k].x + ay[k].y), G * (az[k].x + az[k].y), 0.f);
+        if (accumulate) { const float4 o = acc[i]; a.x += o.x; a.y += o.y; a.z += o.z; }
+        acc[i] = a;
+      }
     }
   }
   if (lane == 0 && inter) atomicAdd(&c->interactions, inter);
@@ -548,8 +575,10 @@ __global__ void iota_kernel(int32_t* ids, int n, int first) {
   if (i < n) ids[i] = first + i;
 }
 
+// m = source tree; g = the tree that owns the targets' walk groups (g == m for an ordinary walk).
 template <int B, bool EPS0>
-int launch_walk(Impl* m, const BHParams& p, const float4* posm, float4* acc, int t0, int t1, cudaStream_t s) {
+int launch_walk(Impl* m, Impl* g, const BHParams& p, const float4* posm, const float4* tgt, float4* acc, int t0, int t1,
+                bool accumulate, cudaStream_t s) {
   int per_sm = 0;
   NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<B, EPS0>, kWalkThreads, 0));
   const int grid = kNumSMsB200 * std::max(1, std::min(per_sm, 8));
@@ -559,8 +588,10 @@ int launch_walk(Impl* m, const BHParams& p, const float4* posm, float4* acc, int
     NB_TRY(realloc_dev(&m->stacks, (size_t)need));
     m->cap_stacks = need;
   }
-  bh_walk_group_kernel<B, EPS0><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, m->groups, m->counters, m->root,
-                                                              p.theta * p.theta, p.eps2, p.G, t0, t1, m->stacks, acc);
+  NB_CUDA(cudaMemsetAsync(&g->counters->next_group, 0, sizeof(int), s));
+  bh_walk_group_kernel<B, EPS0><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, tgt, g->groups, g->counters, m->root,
+                                                              p.theta * p.theta, p.eps2, p.G, t0, t1, accumulate ? 1 : 0,
+                                                              m->stacks, acc);
   return 0;
 }
 
@@ -584,6 +615,8 @@ void bh_free(BHState& st) {
   cudaFree(m->sort.hist); cudaFree(m->sort.tile_sums);
   cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->groups);
   cudaFree(m->counters); cudaFree(m->root); cudaFree(m->stacks); cudaFree(m->boxes);
+  cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_boxes);
+  cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->let_cnt); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);
   delete m;
   st.impl = nullptr;
 }
@@ -623,21 +656,28 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
 
 int bh_forces(BHState& st, const BHParams& p, const float4* posm, float4* acc, int n, int t0, int t1, cudaStream_t s,
               double* launches) {
-  Impl* m = impl_of(st);
-  if (m->n != n || !m->counters) { set_error("Barnes-Hut: forces requested without a tree for these bodies"); return -5; }
+  return bh_forces_from(st, st, p, posm, posm, acc, n, t0, t1, false, s, launches);
+}
+
+int bh_forces_from(BHState& src, BHState& tgt_tree, const BHParams& p, const float4* posm, const float4* tgt, float4* acc, int n,
+                   int t0, int t1, bool accumulate, cudaStream_t s, double* launches) {
+  Impl* m = impl_of(src);
+  Impl* g = impl_of(tgt_tree);
+  if (m->n != n || !m->counters || !g->counters) { set_error("Barnes-Hut: forces requested without a tree for these bodies"); return -5; }
   if (t1 <= t0) return 0;
   const bool eps0 = !(p.eps2 > 0.f);
   if (p.mac == kMacBody) {
+    if (m != g || accumulate) { set_error("Barnes-Hut: the per-body walk (mac = 1) runs on a single tree"); return -1; }
     bh_walk_body_kernel<<<(unsigned)ceil_div(t1 - t0, 128), 128, 0, s>>>(posm, m->node_com, m->node_meta, m->counters, m->root,
                                                                           p.theta, p.eps2, p.G, t0, t1, acc);
   } else {
-    if (m->built_group_size != p.group_size) { set_error("Barnes-Hut: group_size changed since the tree was built"); return -5; }
+    if (g->built_group_size != p.group_size) { set_error("Barnes-Hut: group_size changed since the tree was built"); return -5; }
     const int B = p.group_size / 32;
     int rc = 0;
-    if (eps0) rc = B == 1 ? launch_walk<1, true>(m, p, posm, acc, t0, t1, s) : B == 2 ? launch_walk<2, true>(m, p, posm, acc, t0, t1, s)
-                                                                                      : launch_walk<4, true>(m, p, posm, acc, t0, t1, s);
-    else rc = B == 1 ? launch_walk<1, false>(m, p, posm, acc, t0, t1, s) : B == 2 ? launch_walk<2, false>(m, p, posm, acc, t0, t1, s)
-                                                                                   : launch_walk<4, false>(m, p, posm, acc, t0, t1, s);
+    if (eps0) rc = B == 1 ? launch_walk<1, true>(m, g, p, posm, tgt, acc, t0, t1, accumulate, s) : B == 2 ? launch_walk<2, true>(m, g, p, posm, tgt, acc, t0, t1, accumulate, s)
+                                                                                      : launch_walk<4, true>(m, g, p, posm, tgt, acc, t0, t1, accumulate, s);
+    else rc = B == 1 ? launch_walk<1, false>(m, g, p, posm, tgt, acc, t0, t1, accumulate, s) : B == 2 ? launch_walk<2, false>(m, g, p, posm, tgt, acc, t0, t1, accumulate, s)
+                                                                                   : launch_walk<4, false>(m, g, p, posm, tgt, acc, t0, t1, accumulate, s);
     NB_TRY(rc);
   }
   *launches += 1;
@@ -687,6 +727,306 @@ int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t
   const int64_t k = std::min<int64_t>(count, want);
   if (boxes7 && k > 0) NB_CUDA(cudaMemcpy(boxes7, m->boxes, (size_t)k * 7 * sizeof(float), cudaMemcpyDeviceToHost));
   *n_boxes = count;
+  return 0;
+}
+
+
+// =====================================================================================================================
+// K9 - multi-GPU Barnes-Hut: Morton domain split, body migration and locally-essential-tree (LET) exchange.
+//
+// Every rank owns a contiguous range of the GLOBAL Morton order (keys are taken in one root cube shared by all ranks).
+// Per step:  (1) keys of the local bodies, regular key samples -> all-gather -> W-1 splitters (equal-count quantiles);
+//            (2) bodies are bucketed by destination rank (one 8-bit radix pass) and exchanged (all-to-all-v);
+//            (3) the local tree is built over the bodies now owned;
+//            (4) each rank publishes kLetBoxes boxes around chunks of its bodies; for every peer the local tree is
+//                descended generation by generation with the reference's acceptance rule taken against the NEAREST of
+//                that peer's boxes (so it holds for every body of the peer): accepted cells are exported as point
+//                masses, opened leaves as bodies;
+//            (5) export lists are exchanged (all-to-all-v); the received points get their own tree;
+//            (6) every local walk group is walked through the local tree and then through the LET tree.
+// The reference has no counterpart (it is single threaded); forces equal the single-GPU walk up to the (stricter)
+// acceptance of remote cells and summation order.
+// =====================================================================================================================
+namespace {
+
+__global__ void let_sample_kernel(const uint64_t* __restrict__ keys, const int n, uint64_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kLetSamples) return;
+  out[i] = n > 0 ? keys[(int)(((long long)i * n + n / 2) / kLetSamples) < n ? (int)(((long long)i * n + n / 2) / kLetSamples) : n - 1] : ~0ull;
+}
+
+// One CTA: sort the world * kLetSamples gathered samples (bitonic, shared memory) and take the equal-count quantiles.
+__global__ void __launch_bounds__(1024)
+let_splitters_kernel(const uint64_t* __restrict__ samples, const int world, uint64_t* __restrict__ splitters) {
+  extern __shared__ uint64_t sk[];
+  const int total = world * kLetSamples;
+  int pow2 = 1;
+  while (pow2 < total) pow2 <<= 1;
+  for (int i = threadIdx.x; i < pow2; i += blockDim.x) sk[i] = i < total ? samples[i] : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= pow2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < pow2; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint64_t a = sk[i], b = sk[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int r = threadIdx.x + 1; r < world; r += blockDim.x) splitters[r - 1] = sk[r * kLetSamples];
+}
+
+// keys[i] <- destination rank of body i = number of splitters <= key (bodies with equal keys stay together).
+__global__ void __launch_bounds__(256)
+let_dest_kernel(uint64_t* __restrict__ keys, const int n, const uint64_t* __restrict__ splitters, const int world) {
+  __shared__ uint64_t sp[kMaxWorld];
+  if (threadIdx.x < world - 1) sp[threadIdx.x] = splitters[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = keys[i];
+  int d = 0;
+  for (int r = 0; r < world - 1; r++) d += sp[r] <= k ? 1 : 0;
+  keys[i] = (uint64_t)d;
+}
+
+// send_off[r] = first position in the destination-sorted array whose destination is >= r.
+__global__ void let_offsets_kernel(const uint64_t* __restrict__ dest_sorted, const int n, const int world, int* __restrict__ send_off) {
+  const int r = threadIdx.x;
+  if (r > world) return;
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (dest_sorted[mid] < (uint64_t)r) lo = mid + 1; else hi = mid; }
+  send_off[r] = lo;
+}
+
+// Box b = bounding box of the b-th of kLetBoxes equal chunks of the (Morton-sorted) local bodies; empty chunks get an
+// inverted box that is infinitely far from everything.
+__global__ void __launch_bounds__(256)
+let_boxes_kernel(const float4* __restrict__ posm, const int n, float* __restrict__ boxes6) {
+  const int b = blockIdx.x;
+  const int lo = (int)((long long)n * b / kLetBoxes), hi = (int)((long long)n * (b + 1) / kLetBoxes);
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float4 p = posm[i];
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+  __shared__ float s[8][6];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    }
+  if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; k++) { s[threadIdx.x >> 5][k] = mn[k]; s[threadIdx.x >> 5][3 + k] = mx[k]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; q++) for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], s[q][k]); mx[k] = fmaxf(mx[k], s[q][3 + k]); }
+    for (int k = 0; k < 3; k++) { boxes6[b * 6 + k] = mn[k]; boxes6[b * 6 + 3 + k] = mx[k]; }
+  }
+}
+
+// One generation of the export descent, all peers at once. visit[node] = bit mask of the peers that reached this node.
+__global__ void __launch_bounds__(256)
+let_export_kernel(const int gen, const float4* __restrict__ posm, const float4* __restrict__ node_com,
+                  const int4* __restrict__ node_meta, const Counters* __restrict__ c, const float4* __restrict__ root,
+                  const float* __restrict__ peer_boxes, const int world, const int rank, const float theta2,
+                  uint32_t* __restrict__ visit, float4* __restrict__ let_out, int* __restrict__ let_cnt, const int cap_let) {
+  const int gb = c->gen_off[gen], ge = c->gen_off[gen + 1];
+  const float root_half = root[0].w;
+  for (int node = gb + blockIdx.x * blockDim.x + threadIdx.x; node < ge; node += gridDim.x * blockDim.x) {
+    const uint32_t mask = node == 0 ? (((1u << world) - 1u) & ~(1u << rank)) : visit[node];
+    const int4 m = node_meta[node];
+    const bool leaf = (m.z & kLeafFlag) != 0;
+    uint32_t down = 0;
+    if (mask) {
+      const float4 cm = node_com[node];
+      const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);
+      for (int p = 0; p < world; p++) {
+        if (!(mask >> p & 1u)) continue;
+        const float* bx = peer_boxes + (size_t)p * kLetBoxes * 6;
+        float dmin2 = 3.0e38f;
+        for (int b = 0; b < kLetBoxes; b++) {
+          const float dx = fmaxf(fmaxf(bx[b * 6] - cm.x, cm.x - bx[b * 6 + 3]), 0.f);
+          const float dy = fmaxf(fmaxf(bx[b * 6 + 1] - cm.y, cm.y - bx[b * 6 + 4]), 0.f);
+          const float dz = fmaxf(fmaxf(bx[b * 6 + 2] - cm.z, cm.z - bx[b * 6 + 5]), 0.f);
+          dmin2 = fminf(dmin2, dx * dx + dy * dy + dz * dz);
+        }
+        if (size * size < theta2 * dmin2 || (leaf && m.y == 1)) {
+          const int slot = atomicAdd(let_cnt + p, 1);
+          if (slot < cap_let) let_out[(size_t)p * cap_let + slot] = cm;
+        } else if (leaf) {
+          const int slot = atomicAdd(let_cnt + p, m.y);
+          for (int k = 0; k < m.y; k++) if (slot + k < cap_let) let_out[(size_t)p * cap_let + slot + k] = posm[m.x + k];
+        } else {
+          down |= 1u << p;
+        }
+      }
+    }
+    if (!leaf) for (int k = 0; k < m.y; k++) visit[m.x + k] = down;
+  }
+}
+
+int let_ensure(Impl* m, int world, int64_t cap_local, cudaStream_t s) {
+  if (m->let_world != world) {
+    NB_CUDA(cudaStreamSynchronize(s));
+    NB_TRY(realloc_dev(&m->samples, (size_t)(world + 1) * kLetSamples));
+    NB_TRY(realloc_dev(&m->splitters, (size_t)world));
+    NB_TRY(realloc_dev(&m->send_off, (size_t)world + 1));
+    NB_TRY(realloc_dev(&m->all_off, (size_t)world * (world + 1)));
+    NB_TRY(realloc_dev(&m->peer_boxes, (size_t)world * kLetBoxes * 6));
+    NB_TRY(realloc_dev(&m->let_cnt, (size_t)world));
+    m->let_world = world;
+  }
+  if (cap_local > m->cap_let) {
+    NB_CUDA(cudaStreamSynchronize(s));
+    NB_TRY(realloc_dev(&m->let_out, (size_t)world * (size_t)cap_local));
+    m->cap_let = cap_local;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// Phases (1)-(2): on return the first *n_local entries of posm_a / vel_a / ids_a hold the bodies this rank owns now
+// (`world` runs received from the peers, not yet sorted). posm_b / vel_b / ids_b are scratch (send staging).
+int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
+                   float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local,
+                   cudaStream_t s, double* launches) {
+  Impl* m = impl_of(st);
+  const int world = comm->world(), rank = comm->rank();
+  if (world > kMaxWorld) { set_error("Barnes-Hut LET: at most 16 ranks"); return -1; }
+  NB_TRY(ensure(m, (int)std::max<int64_t>(cap, 1), s));
+  NB_TRY(let_ensure(m, world, cap, s));
+  const unsigned nb = (unsigned)ceil_div(std::max(n, 1), 256);
+  root_cube_kernel<<<1, 1, 0, s>>>(box_global, p.reference_root ? 1 : 0, m->root);
+  if (n > 0) morton_kernel<<<nb, 256, 0, s>>>(posm_a, n, m->root, m->sort.keys[0]);
+  let_sample_kernel<<<1, kLetSamples, 0, s>>>(m->sort.keys[0], n, m->samples + (size_t)world * kLetSamples);
+  NB_TRY(comm->all_gather_bytes(m->samples + (size_t)world * kLetSamples, m->samples, (size_t)kLetSamples * 8, s));
+  int pow2 = 1;
+  while (pow2 < world * kLetSamples) pow2 <<= 1;
+  let_splitters_kernel<<<1, 1024, (size_t)pow2 * 8, s>>>(m->samples, world, m->splitters);
+  *launches += 4;
+  int sorted = 0;
+  if (n > 0) {
+    let_dest_kernel<<<nb, 256, 0, s>>>(m->sort.keys[0], n, m->splitters, world);
+    sorted = radix_sort_pairs(m->sort, n, 8, s, launches);     // one pass: stable bucket by destination rank
+    gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[sorted], n, posm_a, vel_a, ids_a, posm_b, vel_b, ids_b);
+    *launches += 2;
+  }
+  let_offsets_kernel<<<1, 32, 0, s>>>(m->sort.keys[sorted], n, world, m->send_off);
+  NB_TRY(comm->all_gather_bytes(m->send_off, m->all_off, (size_t)(world + 1) * 4, s));
+  std::vector<int> off((size_t)world * (world + 1));
+  NB_CUDA(cudaMemcpyAsync(off.data(), m->all_off, off.size() * 4, cudaMemcpyDeviceToHost, s));
+  NB_CUDA(cudaStreamSynchronize(s));
+  size_t sb[kMaxWorld], so[kMaxWorld], rb[kMaxWorld], ro[kMaxWorld];
+  int64_t total = 0;
+  for (int q = 0; q < world; q++) {
+    const int* mine = off.data() + (size_t)rank * (world + 1);
+    const int* theirs = off.data() + (size_t)q * (world + 1);
+    sb[q] = (size_t)(mine[q + 1] - mine[q]); so[q] = (size_t)mine[q];
+    rb[q] = (size_t)(theirs[rank + 1] - theirs[rank]); ro[q] = (size_t)total;
+    total += (int64_t)rb[q];
+  }
+  if (total > cap) { set_error("Barnes-Hut LET: a rank's domain outgrew its body buffers (" + std::to_string(total) + " > " + std::to_string(cap) + ")"); return -5; }
+  auto exchange = [&](const void* send, void* recv, size_t elem) -> int {
+    size_t a[kMaxWorld], b[kMaxWorld], c2[kMaxWorld], d[kMaxWorld];
+    for (int q = 0; q < world; q++) { a[q] = sb[q] * elem; b[q] = so[q] * elem; c2[q] = rb[q] * elem; d[q] = ro[q] * elem; }
+    return comm->all_to_all_v(send, a, b, recv, c2, d, s);
+  };
+  // destination-sorted bodies sit in *_b; every rank receives its new bodies into *_a
+  NB_TRY(exchange(posm_b, posm_a, 16));
+  NB_TRY(exchange(vel_b, vel_a, 16));
+  NB_TRY(exchange(ids_b, ids_a, 4));
+  *n_local = (int)total;
+  NB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Phases (4)-(5): `local` holds the tree of the n sorted local bodies posm. Builds `let` over the points received from
+// the peers (n_let of them; 0 is possible).
+int bh_let_exchange(BHState& local, BHState& let, Comm* comm, const BHParams& p, const float4* posm, int n,
+                    const uint32_t* box_global, int* n_let, cudaStream_t s, double* launches) {
+  Impl* m = impl_of(local);
+  const int world = comm->world(), rank = comm->rank();
+  NB_TRY(let_ensure(m, world, std::max<int64_t>(m->cap_n, 1024), s));
+  const int64_t need_nodes = std::max<int64_t>(m->cap_nodes, 16);
+  if (need_nodes > m->cap_visit) {
+    NB_CUDA(cudaStreamSynchronize(s));
+    NB_TRY(realloc_dev(&m->visit, (size_t)need_nodes));
+    m->cap_visit = need_nodes;
+  }
+  float* my_boxes = m->peer_boxes + (size_t)rank * kLetBoxes * 6;
+  let_boxes_kernel<<<kLetBoxes, 256, 0, s>>>(posm, n, my_boxes);
+  NB_TRY(comm->all_gather_bytes(my_boxes, m->peer_boxes, (size_t)kLetBoxes * 6 * 4, s));
+  NB_CUDA(cudaMemsetAsync(m->let_cnt, 0, (size_t)world * 4, s));
+  *launches += 1;
+  if (n > 0) {
+    for (int gen = 0; gen <= kMaxLevel; gen++)
+      let_export_kernel<<<kNumSMsB200 * 2, 256, 0, s>>>(gen, posm, m->node_com, m->node_meta, m->counters, m->root, m->peer_boxes,
+                                                        world, rank, p.theta * p.theta, m->visit, m->let_out, m->let_cnt, (int)m->cap_let);
+    *launches += kMaxLevel + 1;
+  }
+  NB_TRY(comm->all_gather_bytes(m->let_cnt, m->all_off, (size_t)world * 4, s));
+  std::vector<int> cnt((size_t)world * world);
+  NB_CUDA(cudaMemcpyAsync(cnt.data(), m->all_off, cnt.size() * 4, cudaMemcpyDeviceToHost, s));
+  NB_CUDA(cudaStreamSynchronize(s));
+  size_t sb[kMaxWorld], so[kMaxWorld], rb[kMaxWorld], ro[kMaxWorld];
+  int64_t total = 0;
+  for (int q = 0; q < world; q++) {
+    const int mine = cnt[(size_t)rank * world + q], theirs = cnt[(size_t)q * world + rank];
+    if (mine > m->cap_let) { set_error("Barnes-Hut LET: export list overflow"); return -5; }
+    sb[q] = (size_t)mine * 16; so[q] = (size_t)q * (size_t)m->cap_let * 16;
+    rb[q] = (size_t)theirs * 16; ro[q] = (size_t)total * 16;
+    total += theirs;
+  }
+  if (total > m->cap_let_in) {
+    const int64_t c = total + total / 4 + 4096;
+    NB_TRY(realloc_dev(&m->let_in, (size_t)c));
+    NB_TRY(realloc_dev(&m->let_sorted, (size_t)c));
+    m->cap_let_in = c;
+  }
+  NB_TRY(comm->all_to_all_v(m->let_out, sb, so, m->let_in, rb, ro, s));
+  *n_let = (int)total;
+  if (total > 0)
+    NB_TRY(bh_build(let, p, m->let_in, nullptr, nullptr, m->let_sorted, nullptr, nullptr, (int)total, box_global, s, launches));
+  NB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+const float4* bh_let_sources(BHState& local) { return impl_of(local)->let_sorted; }
+
+// Diagnostics: every rank's bodies gathered into one array (n_global float4) - the energy sum needs all sources.
+int bh_let_gather_all(BHState& local, Comm* comm, const float4* posm, int n, int64_t n_global, const float4** out, int64_t* first,
+                      cudaStream_t s) {
+  Impl* m = impl_of(local);
+  const int world = comm->world(), rank = comm->rank();
+  NB_TRY(let_ensure(m, world, std::max<int64_t>(m->cap_n, 1024), s));
+  if (n_global > m->cap_all_pos) {
+    NB_CUDA(cudaStreamSynchronize(s));
+    NB_TRY(realloc_dev(&m->all_pos, (size_t)n_global));
+    m->cap_all_pos = n_global;
+  }
+  NB_CUDA(cudaMemcpyAsync(m->send_off, &n, 4, cudaMemcpyHostToDevice, s));
+  NB_TRY(comm->all_gather_bytes(m->send_off, m->all_off, 4, s));
+  std::vector<int> cnt((size_t)world);
+  NB_CUDA(cudaMemcpyAsync(cnt.data(), m->all_off, (size_t)world * 4, cudaMemcpyDeviceToHost, s));
+  NB_CUDA(cudaStreamSynchronize(s));
+  size_t sb[kMaxWorld], so[kMaxWorld], rb[kMaxWorld], ro[kMaxWorld];
+  int64_t total = 0;
+  for (int q = 0; q < world; q++) {
+    sb[q] = (size_t)n * 16; so[q] = 0;
+    rb[q] = (size_t)cnt[(size_t)q] * 16; ro[q] = (size_t)total * 16;
+    if (q == rank) *first = total;
+    total += cnt[(size_t)q];
+  }
+  if (total != n_global) { set_error("Barnes-Hut LET: ranks hold " + std::to_string(total) + " bodies, expected " + std::to_string(n_global)); return -5; }
+  NB_TRY(comm->all_to_all_v(posm, sb, so, m->all_pos, rb, ro, s));
+  *out = m->all_pos;
   return 0;
 }
 

@@ -45,6 +45,22 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
 // Accelerations (G applied) of the sorted bodies [t0, t1) -> acc[t0 .. t1).
 int bh_forces(BHState& st, const BHParams& p, const float4* posm, float4* acc, int n, int t0, int t1, cudaStream_t s,
               double* launches);
+// Same walk with the sources taken from tree `src` (bodies posm, n of them) and the targets / walk groups from
+// `tgt_tree` (bodies tgt); accumulate = add to acc instead of overwriting (second pass over received LET points).
+int bh_forces_from(BHState& src, BHState& tgt_tree, const BHParams& p, const float4* posm, const float4* tgt, float4* acc, int n,
+                   int t0, int t1, bool accumulate, cudaStream_t s, double* launches);
+
+// ---- multi-GPU (K9): Morton domain split + body migration + locally-essential-tree exchange; see bh.cu
+class Comm;
+int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
+                   float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local,
+                   cudaStream_t s, double* launches);
+int bh_let_exchange(BHState& local, BHState& let, Comm* comm, const BHParams& p, const float4* posm, int n,
+                    const uint32_t* box_global, int* n_let, cudaStream_t s, double* launches);
+const float4* bh_let_sources(BHState& local);
+int bh_let_gather_all(BHState& local, Comm* comm, const float4* posm, int n, int64_t n_global, const float4** out, int64_t* first,
+                      cudaStream_t s);
+
 // Synchronises; fills the *_host fields and the interaction count of the last bh_forces.
 int bh_fetch_stats(BHState& st, cudaStream_t s, double* interactions);
 int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t cap, int64_t* n_boxes, cudaStream_t s);

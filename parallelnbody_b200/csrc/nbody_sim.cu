@@ -70,7 +70,7 @@ struct nbody_sim {
   nbody_config cfg;
   bool initialized = false;
   bool show_octree = false;
-  int64_t n_global = 0, n_local = 0, local_begin = 0, n_per = 0;
+  int64_t n_global = 0, n_local = 0, local_begin = 0, n_per = 0, slice_begin = 0;
   int64_t steps = 0;
   double launches = 0;
 
@@ -96,7 +96,9 @@ struct nbody_sim {
 
   Comm* comm = nullptr;
   DirectPlan plan;
-  BHState tree;
+  BHState tree;       // Barnes-Hut: tree over the bodies held by this rank
+  BHState tree_let;   // multi-GPU LET mode: tree over the points received from the peers
+  int n_let = 0;
 
   // timing of the last call
   float ms_call = 0, ms_force = 0, ms_build = 0, ms_integrate = 0, ms_comm = 0;
@@ -106,14 +108,16 @@ struct nbody_sim {
   // Direct sum: posm holds all N sources (this rank's slice at local_begin), vel / acc hold the local slice only.
   // Barnes-Hut: every array holds all N bodies in Morton order; this rank integrates the slice at local_begin.
   bool bh() const { return cfg.method == NBODY_BARNES_HUT; }
+  // multi-GPU Barnes-Hut with domain decomposition: the arrays hold only the bodies this rank owns (n_local varies)
+  bool let_mode() const { return bh() && comm != nullptr && cfg.bh_exchange == 0; }
   float4* posm_local() { return d_posm + local_begin; }
   float4* vel_local() { return d_vel + (bh() ? local_begin : 0); }
   float4* acc_local() { return d_acc + (bh() ? local_begin : 0); }
   int32_t* ids_local() { return d_ids + (bh() ? local_begin : 0); }
   // which bodies a set_* call uploads to this rank, and where they land
-  int64_t load_begin() const { return bh() ? 0 : local_begin; }
-  int64_t load_count() const { return bh() ? n_global : n_local; }
-  float4* posm_load() { return d_posm + load_begin(); }
+  int64_t load_begin() const { return bh() && !let_mode() ? 0 : slice_begin; }
+  int64_t load_count() const { return bh() && !let_mode() ? n_global : n_local; }
+  float4* posm_load() { return d_posm + (bh() ? 0 : slice_begin); }
 };
 
 namespace {
@@ -151,8 +155,9 @@ cudaEvent_t pool_event(nbody_sim* s, size_t k) {
 void partition(nbody_sim* s, int64_t n) {
   s->n_global = n;
   s->n_per = ceil_div(n, s->cfg.world);
-  s->local_begin = std::min<int64_t>(n, (int64_t)s->cfg.rank * s->n_per);
-  s->n_local = std::min<int64_t>(s->n_per, n - s->local_begin);
+  s->slice_begin = std::min<int64_t>(n, (int64_t)s->cfg.rank * s->n_per);
+  s->n_local = std::min<int64_t>(s->n_per, n - s->slice_begin);
+  s->local_begin = s->let_mode() ? 0 : s->slice_begin;   // offset of the rank's bodies inside the device arrays
 }
 
 int reserve_state(nbody_sim* s) {
@@ -166,7 +171,8 @@ int reserve_state(nbody_sim* s) {
     NB_TRY(dev_reserve(&s->d_acc, &s->cap_acc, std::max<int64_t>(s->n_local, 1), s->stream));
     NB_TRY(dev_reserve(&s->d_ids, &s->cap_ids, std::max<int64_t>(s->n_local, 1), s->stream));
   } else {
-    const int64_t total = std::max<int64_t>(s->n_per * s->cfg.world, 1);   // padded so the slices all-gather in place
+    // replicated: all bodies, padded so the slices all-gather in place; LET: the rank's domain with room to grow
+    const int64_t total = s->let_mode() ? 2 * s->n_per + 4096 : std::max<int64_t>(s->n_per * s->cfg.world, 1);
     NB_TRY(dev_reserve(&s->d_posm, &s->cap_posm, total, s->stream));
     NB_TRY(dev_reserve(&s->d_vel, &s->cap_vel, total, s->stream));
     NB_TRY(dev_reserve(&s->d_acc, &s->cap_acc, total, s->stream));
@@ -229,16 +235,17 @@ int launch_direct(nbody_sim* s) {
 int launch_cube_size(nbody_sim* s) {
   static const uint32_t init[8] = {0u, ~0u, ~0u, ~0u, 0u, 0u, 0u, 0u};
   NB_CUDA(cudaMemcpyAsync(s->d_box, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
-  // Barnes-Hut keeps all N bodies on every rank: reduce over them locally, no collective
-  const float4* src = s->bh() ? s->d_posm : s->posm_local();
-  const int64_t cnt = s->bh() ? s->n_global : s->n_local;
+  // replicated Barnes-Hut keeps all N bodies on every rank: reduce over them locally, no collective
+  const bool all_here = s->bh() && !s->let_mode();
+  const float4* src = all_here ? s->d_posm : s->posm_local();
+  const int64_t cnt = all_here ? s->n_global : s->n_local;
   if (cnt > 0) {
     const int blocks = (int)std::min<int64_t>(ceil_div(cnt, 256), kNumSMsB200 * 8);
     cube_size_kernel<<<blocks, 256, 0, s->stream>>>(src, (int)cnt, s->d_box);
     s->launches++;
     NB_CUDA(cudaGetLastError());
   }
-  if (s->comm && !s->bh()) {
+  if (s->comm && !all_here) {
     NB_TRY(s->comm->all_reduce_u32_max(s->d_box, 1, s->stream));
     NB_TRY(s->comm->all_reduce_u32_min(s->d_box + 1, 3, s->stream));
     NB_TRY(s->comm->all_reduce_u32_max(s->d_box + 4, 3, s->stream));
@@ -246,12 +253,12 @@ int launch_cube_size(nbody_sim* s) {
   return 0;
 }
 
-// One force evaluation (+ integration when dt > 0) enqueued on the stream. ev: optional 5 events
-// (start, after build, after force, after integrate, after comm).
+// One force evaluation (+ integration when dt > 0) enqueued on the stream. ev: optional 6 events
+// (0 start, 1 after build, 5 after the pre-force exchange, 2 after force, 3 after integrate, 4 after the post-step exchange).
 int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
   if (ev) NB_CUDA(cudaEventRecord(ev[0], s->stream));
   if (s->cfg.method == NBODY_DIRECT) {
-    if (ev) NB_CUDA(cudaEventRecord(ev[1], s->stream));
+    if (ev) { NB_CUDA(cudaEventRecord(ev[1], s->stream)); NB_CUDA(cudaEventRecord(ev[5], s->stream)); }
     NB_TRY(launch_direct(s));
     if (ev) NB_CUDA(cudaEventRecord(ev[2], s->stream));
     if (s->n_local > 0) {
@@ -275,6 +282,40 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
     bp.group_size = s->cfg.group_size;
     bp.group_pack = s->cfg.group_pack;
     double launches = 0;
+    if (s->let_mode()) {
+      // (1)-(2) splitters + body migration, (3) local tree, (4)-(5) LET exchange + tree, (6) two walks; see bh.cu K9
+      int n_new = 0;
+      NB_TRY(bh_let_migrate(s->tree, s->comm, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local,
+                            std::min(s->cap_posm, s->cap_posm2), s->d_box, &n_new, s->stream, &launches));
+      s->n_local = n_new;
+      if (s->n_local > 0) {
+        NB_TRY(bh_build(s->tree, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local, s->d_box,
+                        s->stream, &launches));
+        std::swap(s->d_posm, s->d_posm2); std::swap(s->cap_posm, s->cap_posm2);
+        std::swap(s->d_vel, s->d_vel2);   std::swap(s->cap_vel, s->cap_vel2);
+        std::swap(s->d_ids, s->d_ids2);   std::swap(s->cap_ids, s->cap_ids2);
+      }
+      s->ids_identity = false;
+      if (ev) NB_CUDA(cudaEventRecord(ev[1], s->stream));
+      NB_TRY(bh_let_exchange(s->tree, s->tree_let, s->comm, bp, s->d_posm, (int)s->n_local, s->d_box, &s->n_let, s->stream, &launches));
+      if (ev) NB_CUDA(cudaEventRecord(ev[5], s->stream));   // [1]..[5] = LET exchange, reported as comm
+      if (s->n_local > 0) {
+        NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
+        if (s->n_let > 0)
+          NB_TRY(bh_forces_from(s->tree_let, s->tree, bp, bh_let_sources(s->tree), s->d_posm, s->d_acc, s->n_let, 0, (int)s->n_local,
+                                true, s->stream, &launches));
+      }
+      s->launches += launches;
+      if (ev) NB_CUDA(cudaEventRecord(ev[2], s->stream));
+      if (integrate && s->n_local > 0) {
+        kick_drift_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>((int)s->n_local, dt, s->d_posm, s->d_vel, s->d_acc);
+        s->launches++;
+        NB_CUDA(cudaGetLastError());
+      }
+      if (ev) { NB_CUDA(cudaEventRecord(ev[3], s->stream)); NB_CUDA(cudaEventRecord(ev[4], s->stream)); }
+      if (integrate) s->steps++;
+      return 0;
+    }
     // Morton reordering of ALL bodies (identical on every rank: same data, stable sort), tree + monopoles
     NB_TRY(bh_build(s->tree, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_global, s->d_box,
                     s->stream, &launches));
@@ -282,7 +323,7 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
     std::swap(s->d_vel, s->d_vel2);   std::swap(s->cap_vel, s->cap_vel2);
     std::swap(s->d_ids, s->d_ids2);   std::swap(s->cap_ids, s->cap_ids2);
     s->ids_identity = false;
-    if (ev) NB_CUDA(cudaEventRecord(ev[1], s->stream));
+    if (ev) { NB_CUDA(cudaEventRecord(ev[1], s->stream)); NB_CUDA(cudaEventRecord(ev[5], s->stream)); }
     // this rank walks and integrates its slice of the Morton order (a compact spatial domain)
     const int t0 = (int)s->local_begin, t1 = (int)(s->local_begin + s->n_local);
     NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_global, t0, t1, s->stream, &launches));
@@ -310,9 +351,9 @@ int run_steps(nbody_sim* s, float dt, int nsteps, bool integrate, bool sync) {
   const int timed = sync ? std::min(nsteps, 128) : 0;
   NB_CUDA(cudaEventRecord(s->ev0, s->stream));
   for (int k = 0; k < nsteps; k++) {
-    cudaEvent_t ev[5];
+    cudaEvent_t ev[6];
     bool use = k < timed;
-    if (use) for (int q = 0; q < 5; q++) { ev[q] = pool_event(s, (size_t)k * 5 + q); if (!ev[q]) use = false; }
+    if (use) for (int q = 0; q < 6; q++) { ev[q] = pool_event(s, (size_t)k * 6 + q); if (!ev[q]) use = false; }
     NB_TRY(enqueue_step(s, dt, integrate, use ? ev : nullptr));
   }
   NB_CUDA(cudaEventRecord(s->ev1, s->stream));
@@ -321,13 +362,14 @@ int run_steps(nbody_sim* s, float dt, int nsteps, bool integrate, bool sync) {
   NB_CUDA(cudaEventElapsedTime(&s->ms_call, s->ev0, s->ev1));
   s->ms_build = s->ms_force = s->ms_integrate = s->ms_comm = 0;
   for (int k = 0; k < timed; k++) {
-    float a = 0, b = 0, c = 0, d = 0;
-    cudaEvent_t* e = &s->ev_pool[(size_t)k * 5];
+    float a = 0, b = 0, c = 0, d = 0, x = 0;
+    cudaEvent_t* e = &s->ev_pool[(size_t)k * 6];
     NB_CUDA(cudaEventElapsedTime(&a, e[0], e[1]));
-    NB_CUDA(cudaEventElapsedTime(&b, e[1], e[2]));
+    NB_CUDA(cudaEventElapsedTime(&x, e[1], e[5]));
+    NB_CUDA(cudaEventElapsedTime(&b, e[5], e[2]));
     NB_CUDA(cudaEventElapsedTime(&c, e[2], e[3]));
     NB_CUDA(cudaEventElapsedTime(&d, e[3], e[4]));
-    s->ms_build += a; s->ms_force += b; s->ms_integrate += c; s->ms_comm += d;
+    s->ms_build += a; s->ms_force += b; s->ms_integrate += c; s->ms_comm += d + x;
   }
   if (timed > 0 && timed < nsteps) {  // scale the sampled phases to the whole call
     const float f = (float)nsteps / (float)timed;
@@ -342,10 +384,13 @@ int stage_reserve(nbody_sim* s, int64_t bytes) { return dev_reserve(&s->d_stage,
 int finish_set(nbody_sim* s) {
   s->ids_identity = true;
   if (s->bh()) {
-    bh_iota(s->d_ids, (int)s->n_global, 0, s->stream);
+    if (s->let_mode()) bh_iota(s->d_ids, (int)s->n_local, (int)s->slice_begin, s->stream);
+    else bh_iota(s->d_ids, (int)s->n_global, 0, s->stream);
     s->launches++;
   }
   bh_reset(s->tree, s->stream);
+  bh_reset(s->tree_let, s->stream);
+  s->n_let = 0;
   NB_TRY(publish_positions(s));
   NB_CUDA(cudaStreamSynchronize(s->stream));
   s->initialized = true;
@@ -399,6 +444,7 @@ int nbody_config_default(nbody_config* cfg) {
   cfg->mac = 0;
   cfg->group_size = 64;
   cfg->group_pack = 2;
+  cfg->bh_exchange = 0;
   return NBODY_OK;
 }
 
@@ -418,6 +464,8 @@ int nbody_create(nbody_sim** out, const nbody_config* cfg) {
   if (cfg->group_size != 32 && cfg->group_size != 64 && cfg->group_size != 128) return invalid("group_size must be 32, 64 or 128");
   if (cfg->leaf_size < 1 || cfg->leaf_size > 64) return invalid("leaf_size must be in [1, 64]");
   if (cfg->group_pack < 1 || cfg->group_pack > 64) return invalid("group_pack must be in [1, 64]");
+  if (cfg->bh_exchange != 0 && cfg->bh_exchange != 1) return invalid("bh_exchange must be 0 (domain split + LET) or 1 (replicated tree)");
+  if (cfg->method == NBODY_BARNES_HUT && cfg->world > 16) return invalid("Barnes-Hut runs on at most 16 ranks");
   NB_TRY(check_device(cfg->device));
   nbody_sim* s = new nbody_sim();
   s->cfg = *cfg;
@@ -445,6 +493,7 @@ void nbody_destroy(nbody_sim* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   delete s->comm;
   bh_free(s->tree);
+  bh_free(s->tree_let);
   cudaFree(s->d_posm2); cudaFree(s->d_vel2); cudaFree(s->d_ids2);
   cudaFree(s->d_posm); cudaFree(s->d_vel); cudaFree(s->d_acc); cudaFree(s->d_partial); cudaFree(s->d_ids);
   cudaFree(s->d_stage); cudaFree(s->d_box); cudaFree(s->d_energy);
@@ -664,10 +713,13 @@ int nbody_energy(nbody_sim* s, double* ke, double* pe) {
   if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
   NB_CUDA(cudaSetDevice(s->cfg.device));
   NB_CUDA(cudaMemsetAsync(s->d_energy, 0, 2 * sizeof(double), s->stream));
+  // sources = all N bodies; local body i sits at source index first + i (what the self-pair exclusion needs). Direct and
+  // replicated Barnes-Hut keep them in d_posm; in LET mode they are gathered from the ranks (a collective: every rank calls).
+  const float4* src = s->d_posm;
+  int64_t first = s->local_begin;
+  if (s->let_mode()) NB_TRY(bh_let_gather_all(s->tree, s->comm, s->d_posm, (int)s->n_local, s->n_global, &src, &first, s->stream));
   if (s->n_local > 0) {
-    // sources = all N bodies (both methods keep them in d_posm); local body i sits at source index local_begin + i,
-    // which is what the self-pair exclusion needs
-    energy_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(s->d_posm, (int)s->n_global, s->posm_local(), s->vel_local(), (int)s->n_local, s->local_begin, s->cfg.G, s->cfg.eps * s->cfg.eps, s->d_energy);
+    energy_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(src, (int)s->n_global, s->posm_local(), s->vel_local(), (int)s->n_local, first, s->cfg.G, s->cfg.eps * s->cfg.eps, s->d_energy);
     s->launches++;
     NB_CUDA(cudaGetLastError());
   }

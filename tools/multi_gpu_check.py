@@ -10,7 +10,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import parallelnbody_b200 as P  # noqa: E402
-from parallelnbody_b200 import ic  # noqa: E402
+from parallelnbody_b200 import ic, launch  # noqa: E402
 
 
 def rel_l2(a, b):
@@ -30,36 +30,44 @@ def main():
         return bytes(t.cpu().numpy().tobytes())
 
     ok = True
-    for method, n, steps, tol in ((P.METHOD_DIRECT, 50_001, 10, 2e-6), (P.METHOD_BARNES_HUT, 200_003, 10, 1e-6)):
+    # (method, bh_exchange, n, steps, position tolerance vs the single-GPU run)
+    cases = ((P.METHOD_DIRECT, 0, 50_001, 10, 2e-6),       # same kernel, bit-identical in practice
+             (P.METHOD_BARNES_HUT, 1, 200_003, 10, 1e-6),  # replicated tree: same tree, same groups
+             (P.METHOD_BARNES_HUT, 0, 200_003, 10, 2e-5))  # domain split + LET: remote cells accepted more strictly
+    for method, exch, n, steps, tol in cases:
         posm, vel = ic.plummer(n, seed=5)
         uid = fresh_uid()
-        with P.OctreeSearch(method=method, eps=0.01, theta=0.3, device=local, rank=rank, world=world, nccl_unique_id=uid) as s:
+        with P.OctreeSearch(method=method, eps=0.01, theta=0.3, device=local, rank=rank, world=world, nccl_unique_id=uid,
+                            bh_exchange=exch) as s:
             s.SetBodies(posm, vel)
             ke, pe = s.Energy()
+            s.CreateOctree()
+            ids0 = s.LocalIds()
+            acc0 = launch.combine_shares(s.Accelerations(), ids0, n, dist, device="cuda")
             s.Step(1e-3, steps)
-            mine_p, mine_v = s.Positions(), s.Velocities()
             ids = s.LocalIds()
+            full_p = launch.combine_shares(s.Positions(), ids, n, dist, device="cuda")
+            full_v = launch.combine_shares(s.Velocities(), ids, n, dist, device="cuda")
             st = s.Stats()
-        # combine the ranks' disjoint shares
-        full_p = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
-        full_v = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
-        cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
-        idt = torch.from_numpy(ids).cuda()
-        full_p[idt] = torch.from_numpy(mine_p[ids]).cuda()
-        full_v[idt] = torch.from_numpy(mine_v[ids]).cuda()
-        cnt[idt] += 1
-        for x in (full_p, full_v, cnt):
-            dist.all_reduce(x)
+            nloc = torch.tensor([float(st["n_local"])], device="cuda"); nmax = nloc.clone(); nmin = nloc.clone()
+            dist.all_reduce(nmax, op=dist.ReduceOp.MAX); dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
         if rank == 0:
             with P.OctreeSearch(method=method, eps=0.01, theta=0.3, device=local) as one:
                 one.SetBodies(posm, vel)
                 ke1, pe1 = one.Energy()
+                one.CreateOctree()
+                a1 = one.Accelerations()
                 one.Step(1e-3, steps)
                 p1, v1 = one.Positions(), one.Velocities()
-            ep, ev = rel_l2(full_p.cpu().numpy(), p1), rel_l2(full_v.cpu().numpy(), v1)
-            good = bool((cnt == 1).all().item()) and ep <= tol and ev <= 50 * tol and abs(ke - ke1) <= 1e-9 * abs(ke1) and abs(pe - pe1) <= 1e-6 * abs(pe1)
-            print(f"method={method} world={world} n={n}: pos rel-L2 {ep:.2e} vel rel-L2 {ev:.2e} energy {ke + pe:.6e} vs {ke1 + pe1:.6e} "
-                  f"ms_comm {st['ms_comm']:.3f} ms_force {st['ms_force']:.3f} -> {'ok' if good else 'MISMATCH'}", flush=True)
+            with P.OctreeSearch(method=P.METHOD_DIRECT, eps=0.01, device=local) as d:
+                d.SetBodies(posm, vel); d.CreateOctree(); exact = d.Accelerations()
+            ep, ev = rel_l2(full_p, p1), rel_l2(full_v, v1)
+            err_multi, err_one = rel_l2(acc0, exact), rel_l2(a1, exact)
+            good = (ep <= tol and ev <= 50 * tol and abs(ke - ke1) <= 1e-9 * abs(ke1) and abs(pe - pe1) <= 1e-6 * abs(pe1)
+                    and err_multi <= err_one * 1.05 + 1e-6)
+            print(f"method={method} exchange={exch} world={world} n={n}: pos rel-L2 {ep:.2e} vel rel-L2 {ev:.2e} | force error vs direct: "
+                  f"{err_multi:.3e} (multi) {err_one:.3e} (1 GPU) | energy {ke + pe:.6e} vs {ke1 + pe1:.6e} | n_local {int(nmin.item())}..{int(nmax.item())} "
+                  f"| ms/step force {st['ms_force'] / steps:.3f} build {st['ms_build'] / steps:.3f} comm {st['ms_comm'] / steps:.3f} -> {'ok' if good else 'MISMATCH'}", flush=True)
             ok = ok and good
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
