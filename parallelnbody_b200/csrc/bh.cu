@@ -14,12 +14,16 @@
 //   the reference's `Size` (h:70-74).
 #include "bh.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <vector>
 
 #include "comm.h"
 #include "direct_kernels.cuh"
 #include "radix_sort.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace nbody {
 namespace {
@@ -65,7 +69,8 @@ struct Impl {
   uint64_t* splitters = nullptr;   // [world - 1]
   int* send_off = nullptr;         // [world + 1] body ranges per destination rank
   int* all_off = nullptr;          // [world * (world + 1)] every rank's send_off / LET counts
-  float* peer_boxes = nullptr;     // [world * kLetBoxes * 6] (min xyz, max xyz) of each rank's body chunks
+  float* peer_boxes = nullptr;     // [world * kLetBoxes * 6] (min xyz, max xyz) of each rank's domain cells
+  int2* cut = nullptr;             // [kLetBoxes] body ranges of the local tree cells behind this rank's boxes
   uint32_t* visit = nullptr;       // per node: which peers still descend through it
   int64_t cap_visit = 0;
   float4* let_out = nullptr;       // [world * cap_let] per-peer export lists
@@ -219,15 +224,15 @@ __global__ void tree_init_kernel(const uint64_t* __restrict__ keys, const int n,
   if (n <= super) emit_groups(0, n, group_size, groups, c);
 }
 
-// One generation of the top-down split: every node created by the previous generation either becomes a leaf or is cut
-// at its level's octant digit into its non-empty children (8 lanes per node, one octant boundary each, found by
-// binary search in the sorted keys). Equivalent of the recursive re-insertion in Octree::Add (OctreeSearch.h:65-78).
-__global__ void __launch_bounds__(256)
-tree_split_kernel(const int gen, const uint64_t* __restrict__ keys, const int leaf_size, const int group_size, const int super,
-                  int2* __restrict__ range,
-                  int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
-                  Counters* __restrict__ c) {
-  const int gb = c->gen_off[gen], ge = c->gen_off[gen + 1];
+// The top-down split, all generations in ONE cooperative launch (grid-wide barrier between generations): every node
+// created by the previous generation either becomes a leaf or is cut at its level's octant digit into its non-empty
+// children (8 lanes per node, one octant boundary each, found by binary search in the sorted keys). Equivalent of the
+// recursive re-insertion in Octree::Add (OctreeSearch.h:65-78). `levels` = how many levels the keys are sorted to: a cell
+// at that level is a leaf whatever it holds (21 = all 63 key bits).
+__device__ __forceinline__ int split_generation(const int gb, const int ge, const uint64_t* __restrict__ keys, const int leaf_size,
+                                                const int group_size, const int super, const int levels, int2* __restrict__ range,
+                                                int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
+                                                Counters* __restrict__ c) {
   const int lane = threadIdx.x & 31, sub = lane & 7, gshift = lane & ~7;
   const unsigned gmask = 0xffu << gshift;
   const int stride = gridDim.x * blockDim.x / 8;
@@ -236,13 +241,15 @@ tree_split_kernel(const int gen, const uint64_t* __restrict__ keys, const int le
     const int2 r = range[node];
     const int4 m = meta[node];
     const int cnt = r.y - r.x, level = m.z;
-    if (cnt <= leaf_size || level >= kMaxLevel) {
+    if (cnt <= leaf_size || level >= levels) {
       if (sub == 0) {
         meta[node] = make_int4(r.x, cnt, level | kLeafFlag, m.w);
-        // > super bodies in one deepest-level cell (coincident to 2^-21 of the cube): walk them in chunks
+        // > super bodies in one deepest-level cell (coincident to the key resolution): walk them in chunks
         if (cnt > super) emit_groups(r.x, r.y, group_size, groups, c);
       }
-      maxlvl = max(maxlvl, m.w >= 0 ? (meta[m.w].z & 255) + 1 : 0);   // depth of the leaf's cell in the reference's tree
+      int d = m.w >= 0 ? (meta[m.w].z & 255) + 1 : 0;   // depth of the leaf's cell in the reference's tree
+      if (cnt > leaf_size && level < kMaxLevel) d = levels + 1;   // the sort was too shallow for this cell: ask for more next time
+      maxlvl = max(maxlvl, d);
       continue;
     }
     const int shift = 3 * (kMaxLevel - 1 - level);
@@ -263,7 +270,8 @@ tree_split_kernel(const int gen, const uint64_t* __restrict__ keys, const int le
     if (cc > 0) {
       const int child = base + slot;
       range[child] = make_int2(start, next);
-      meta[child] = make_int4(0, 0, cc > 1 ? common_levels(keys[start], keys[next - 1]) : kMaxLevel, node);
+      // smallest cell holding the child's bodies; beyond `levels` the keys are unsorted, so the prefix is only known to there
+      meta[child] = make_int4(0, 0, cc > 1 ? min(common_levels(keys[start], keys[next - 1]), levels) : kMaxLevel, node);
       ready[child] = 0;
     }
     // Walk groups. A cell with more than `super` bodies hands its small children (<= super bodies each) to the walk:
@@ -281,17 +289,26 @@ tree_split_kernel(const int gen, const uint64_t* __restrict__ keys, const int le
     }
     if (sub == 0) meta[node] = make_int4(base, nchild, level, m.w);
   }
-  if (maxlvl) atomicMax(&c->depth, maxlvl);
-  // the last CTA to finish publishes where the next generation ends
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int t = atomicAdd(&c->ticket, 1);
-    if (t == (int)gridDim.x - 1) {
-      c->gen_off[gen + 2] = *((volatile int*)&c->nnodes);
-      c->ticket = 0;
-    }
+  return maxlvl;
+}
+
+__global__ void __launch_bounds__(256)
+tree_split_kernel(const uint64_t* __restrict__ keys, const int leaf_size, const int group_size, const int super, const int levels,
+                  int2* __restrict__ range, int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
+                  Counters* __restrict__ c) {
+  cg::grid_group grid = cg::this_grid();
+  int gb = 0, ge = 1, maxlvl = 0, gen = 0;
+  for (; gen <= kMaxLevel; gen++) {
+    maxlvl = max(maxlvl, split_generation(gb, ge, keys, leaf_size, group_size, super, levels, range, meta, ready, groups, c));
+    grid.sync();
+    const int next = *((volatile int*)&c->nnodes);   // everything this generation created
+    grid.sync();                                     // nobody allocates again before everyone has read it
+    if (blockIdx.x == 0 && threadIdx.x == 0) c->gen_off[gen + 2] = next;
+    gb = ge; ge = next;
+    if (gb == ge) break;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) for (int g = gen + 3; g < kMaxLevel + 4; g++) c->gen_off[g] = ge;
+  if (maxlvl) atomicMax(&c->depth, maxlvl);
 }
 
 // ---- K7: monopoles (Octree::ComputeMass, OctreeSearch.h:83-97) ---------------------------------------------------
@@ -581,6 +598,7 @@ int launch_walk(Impl* m, Impl* g, const BHParams& p, const float4* posm, const f
                 bool accumulate, cudaStream_t s) {
   int per_sm = 0;
   NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<B, EPS0>, kWalkThreads, 0));
+  if (p.leave_sm_slot) per_sm -= 1;   // room for a concurrent stream's kernels (LET exchange overlapped with this walk)
   const int grid = kNumSMsB200 * std::max(1, std::min(per_sm, 8));
   const int64_t need = (int64_t)grid * kWalkWarps * kStackCap;
   if (need > m->cap_stacks) {
@@ -615,7 +633,7 @@ void bh_free(BHState& st) {
   cudaFree(m->sort.hist); cudaFree(m->sort.tile_sums);
   cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->groups);
   cudaFree(m->counters); cudaFree(m->root); cudaFree(m->stacks); cudaFree(m->boxes);
-  cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_boxes);
+  cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_boxes); cudaFree(m->cut);
   cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->let_cnt); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);
   delete m;
   st.impl = nullptr;
@@ -636,7 +654,12 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
   root_cube_kernel<<<1, 1, 0, s>>>(box, p.reference_root ? 1 : 0, m->root);
   morton_kernel<<<nb, 256, 0, s>>>(posm_in, n, m->root, m->sort.keys[0]);
   *launches += 2;
-  m->sorted = radix_sort_pairs(m->sort, n, 3 * kMaxLevel, s, launches);
+  // Sort only as many levels as the tree needs: the last known depth + 3 (a cell at the last sorted level is a leaf
+  // whatever it holds, so a too-small hint costs accuracy nothing, only walk efficiency, and corrects itself through
+  // the depth statistic). The parity configurations (one-body leaves / per-body walk) always sort all 63 bits.
+  int levels = kMaxLevel;
+  if (p.leaf_size > 1 && p.mac == kMacGroup && p.depth_hint > 0) levels = std::min(kMaxLevel, std::max(8, p.depth_hint + 3));
+  m->sorted = radix_sort_pairs(m->sort, n, 3 * kMaxLevel, s, launches, 3 * (kMaxLevel - levels));
   gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[m->sorted], n, posm_in, vel_in, ids_in, posm, vel, ids);
   const uint64_t* keys = m->sort.keys[m->sorted];
   if (p.group_size != 32 && p.group_size != 64 && p.group_size != 128) { set_error("Barnes-Hut: group_size must be 32, 64 or 128"); return -1; }
@@ -644,12 +667,14 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
   const int super = p.group_size * std::max(1, p.group_pack);
   tree_init_kernel<<<1, 1, 0, s>>>(keys, n, p.group_size, super, m->node_range, m->node_meta, m->node_ready, m->groups, m->counters);
   *launches += 2;
-  const int grid = kNumSMsB200 * 4;
-  for (int gen = 0; gen <= kMaxLevel; gen++)
-    tree_split_kernel<<<grid, 256, 0, s>>>(gen, keys, std::max(1, p.leaf_size), p.group_size, super, m->node_range, m->node_meta, m->node_ready,
-                                           m->groups, m->counters);
-  monopole_kernel<<<grid, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
-  *launches += kMaxLevel + 2;
+  {
+    int leaf = std::max(1, p.leaf_size), gs = p.group_size, sup = super, lv = levels;
+    void* args[] = {(void*)&keys, &leaf, &gs, &sup, &lv, &m->node_range, &m->node_meta, &m->node_ready, &m->groups, &m->counters};
+    // co-resident by construction: at most 2 CTAs per SM (1 when another stream's walk shares the SMs)
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(kNumSMsB200 * (p.leave_sm_slot ? 1 : 2)), dim3(256), args, 0, s));
+  }
+  monopole_kernel<<<kNumSMsB200 * 4, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
+  *launches += 2;
   NB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -738,7 +763,7 @@ int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t
 // Per step:  (1) keys of the local bodies, regular key samples -> all-gather -> W-1 splitters (equal-count quantiles);
 //            (2) bodies are bucketed by destination rank (one 8-bit radix pass) and exchanged (all-to-all-v);
 //            (3) the local tree is built over the bodies now owned;
-//            (4) each rank publishes kLetBoxes boxes around chunks of its bodies; for every peer the local tree is
+//            (4) each rank publishes the bounding boxes of kLetBoxes cells of its local tree (a cut below the root); for every peer the local tree is
 //                descended generation by generation with the reference's acceptance rule taken against the NEAREST of
 //                that peer's boxes (so it holds for every body of the peer): accepted cells are exported as point
 //                masses, opened leaves as bodies;
@@ -802,12 +827,33 @@ __global__ void let_offsets_kernel(const uint64_t* __restrict__ dest_sorted, con
   send_off[r] = lo;
 }
 
-// Box b = bounding box of the b-th of kLetBoxes equal chunks of the (Morton-sorted) local bodies; empty chunks get an
-// inverted box that is infinitely far from everything.
+// A rank describes its domain to its peers by the bounding boxes of a CUT of its local tree: starting from the root,
+// the cell with the most bodies is replaced by its children until kLetBoxes cells are reached. Tree cells are spatially
+// compact (a Morton range is not: it can jump across the whole cube), so the boxes hug the bodies.
+__global__ void let_cut_kernel(const int4* __restrict__ meta, const int2* __restrict__ range, const int n, int2* __restrict__ cut) {
+  int node[kLetBoxes], cnt = 0;
+  if (n > 0) node[cnt++] = 0;
+  while (cnt > 0 && cnt < kLetBoxes) {
+    int best = -1, best_bodies = 1;
+    for (int k = 0; k < cnt; k++) {
+      const int4 m = meta[node[k]];
+      const int2 r = range[node[k]];
+      if (!(m.z & kLeafFlag) && r.y - r.x > best_bodies && cnt - 1 + m.y <= kLetBoxes) { best = k; best_bodies = r.y - r.x; }
+    }
+    if (best < 0) break;
+    const int4 m = meta[node[best]];
+    node[best] = m.x;
+    for (int k = 1; k < m.y; k++) node[cnt++] = m.x + k;
+  }
+  for (int k = 0; k < kLetBoxes; k++) cut[k] = k < cnt ? range[node[k]] : make_int2(0, 0);
+}
+
+// Box b = bounding box of the bodies of cut cell b; unused entries get an inverted box that is infinitely far from
+// everything.
 __global__ void __launch_bounds__(256)
-let_boxes_kernel(const float4* __restrict__ posm, const int n, float* __restrict__ boxes6) {
+let_boxes_kernel(const float4* __restrict__ posm, const int2* __restrict__ cut, float* __restrict__ boxes6) {
   const int b = blockIdx.x;
-  const int lo = (int)((long long)n * b / kLetBoxes), hi = (int)((long long)n * (b + 1) / kLetBoxes);
+  const int lo = cut[b].x, hi = cut[b].y;
   float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const float4 p = posm[i];
@@ -830,14 +876,18 @@ let_boxes_kernel(const float4* __restrict__ posm, const int n, float* __restrict
   }
 }
 
-// One generation of the export descent, all peers at once. visit[node] = bit mask of the peers that reached this node.
+// The export descent, all peers at once, all generations in one cooperative launch. visit[node] = bit mask of the
+// peers that reached this node (written by the parent one generation earlier).
 __global__ void __launch_bounds__(256)
-let_export_kernel(const int gen, const float4* __restrict__ posm, const float4* __restrict__ node_com,
+let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com,
                   const int4* __restrict__ node_meta, const Counters* __restrict__ c, const float4* __restrict__ root,
                   const float* __restrict__ peer_boxes, const int world, const int rank, const float theta2,
                   uint32_t* __restrict__ visit, float4* __restrict__ let_out, int* __restrict__ let_cnt, const int cap_let) {
-  const int gb = c->gen_off[gen], ge = c->gen_off[gen + 1];
+  cg::grid_group grid = cg::this_grid();
   const float root_half = root[0].w;
+  for (int gen = 0; gen <= kMaxLevel; gen++) {
+  const int gb = c->gen_off[gen], ge = c->gen_off[gen + 1];
+  if (gb >= ge) break;
   for (int node = gb + blockIdx.x * blockDim.x + threadIdx.x; node < ge; node += gridDim.x * blockDim.x) {
     const uint32_t mask = node == 0 ? (((1u << world) - 1u) & ~(1u << rank)) : visit[node];
     const int4 m = node_meta[node];
@@ -869,6 +919,8 @@ let_export_kernel(const int gen, const float4* __restrict__ posm, const float4* 
     }
     if (!leaf) for (int k = 0; k < m.y; k++) visit[m.x + k] = down;
   }
+  grid.sync();
+  }
 }
 
 int let_ensure(Impl* m, int world, int64_t cap_local, cudaStream_t s) {
@@ -880,6 +932,7 @@ int let_ensure(Impl* m, int world, int64_t cap_local, cudaStream_t s) {
     NB_TRY(realloc_dev(&m->all_off, (size_t)world * (world + 1)));
     NB_TRY(realloc_dev(&m->peer_boxes, (size_t)world * kLetBoxes * 6));
     NB_TRY(realloc_dev(&m->let_cnt, (size_t)world));
+    NB_TRY(realloc_dev(&m->cut, (size_t)kLetBoxes));
     m->let_world = world;
   }
   if (cap_local > m->cap_let) {
@@ -961,15 +1014,18 @@ int bh_let_exchange(BHState& local, BHState& let, Comm* comm, const BHParams& p,
     m->cap_visit = need_nodes;
   }
   float* my_boxes = m->peer_boxes + (size_t)rank * kLetBoxes * 6;
-  let_boxes_kernel<<<kLetBoxes, 256, 0, s>>>(posm, n, my_boxes);
+  let_cut_kernel<<<1, 1, 0, s>>>(m->node_meta, m->node_range, n, m->cut);
+  let_boxes_kernel<<<kLetBoxes, 256, 0, s>>>(posm, m->cut, my_boxes);
   NB_TRY(comm->all_gather_bytes(my_boxes, m->peer_boxes, (size_t)kLetBoxes * 6 * 4, s));
   NB_CUDA(cudaMemsetAsync(m->let_cnt, 0, (size_t)world * 4, s));
   *launches += 1;
   if (n > 0) {
-    for (int gen = 0; gen <= kMaxLevel; gen++)
-      let_export_kernel<<<kNumSMsB200 * 2, 256, 0, s>>>(gen, posm, m->node_com, m->node_meta, m->counters, m->root, m->peer_boxes,
-                                                        world, rank, p.theta * p.theta, m->visit, m->let_out, m->let_cnt, (int)m->cap_let);
-    *launches += kMaxLevel + 1;
+    int w = world, r = rank, cap_let = (int)m->cap_let;
+    float theta2 = p.theta * p.theta;
+    void* args[] = {(void*)&posm, &m->node_com, &m->node_meta, &m->counters, &m->root, &m->peer_boxes, &w, &r, &theta2, &m->visit,
+                    &m->let_out, &m->let_cnt, &cap_let};
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)let_export_kernel, dim3(kNumSMsB200), dim3(256), args, 0, s));
+    *launches += 1;
   }
   NB_TRY(comm->all_gather_bytes(m->let_cnt, m->all_off, (size_t)world * 4, s));
   std::vector<int> cnt((size_t)world * world);

@@ -23,6 +23,8 @@ struct BHParams {
   bool reference_root = false;
   int mac = kMacGroup;
   int group_size = 64;  // bodies per walk group: 32, 64 or 128 (1, 2 or 4 per lane)
+  bool leave_sm_slot = false;  // walk with one CTA per SM fewer than fit, so kernels of another stream can run beside it
+  int depth_hint = 0;          // last known tree depth (0 = unknown): how many key levels the sort has to resolve
   int group_pack = 2;   // cells of <= group_pack * group_size bodies are cut into equal walk groups
 };
 

@@ -9,8 +9,12 @@
 #include "../../include/nbody.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "bh.cuh"
@@ -76,6 +80,8 @@ struct nbody_sim {
 
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t stream_x = nullptr;          // LET mode: exchange stream, runs beside the local walk
+  cudaEvent_t ev_built = nullptr, ev_let = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_pool;
 
@@ -281,13 +287,36 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
     bp.mac = s->cfg.mac;
     bp.group_size = s->cfg.group_size;
     bp.group_pack = s->cfg.group_pack;
+    bp.depth_hint = s->tree.depth_host;
     double launches = 0;
     if (s->let_mode()) {
       // (1)-(2) splitters + body migration, (3) local tree, (4)-(5) LET exchange + tree, (6) two walks; see bh.cu K9
+      // NBODY_LET_TRACE=1: synchronise after every phase and print host-clock phase times (development aid)
+      static const bool trace = getenv("NBODY_LET_TRACE") != nullptr;
+      auto t_prev = std::chrono::steady_clock::now();
+      auto lap = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[let rank %d step %lld] %-14s %8.3f ms  n_local=%lld n_let=%d\n", s->cfg.rank, (long long)s->steps, what,
+                std::chrono::duration<double, std::milli>(now - t_prev).count(), (long long)s->n_local, s->n_let);
+        t_prev = now;
+      };
+      lap("cube");
+      // NBODY_LET_EVENTS=1: GPU timeline of the step from CUDA events on both streams (printed after a final sync)
+      static const bool evtrace = getenv("NBODY_LET_EVENTS") != nullptr;
+      std::vector<std::pair<const char*, cudaEvent_t>> marks;
+      auto mark = [&](const char* what, cudaStream_t st) {
+        if (!evtrace) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.push_back({what, e});
+      };
+      mark("start(after cube)", s->stream);
       int n_new = 0;
       NB_TRY(bh_let_migrate(s->tree, s->comm, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local,
                             std::min(s->cap_posm, s->cap_posm2), s->d_box, &n_new, s->stream, &launches));
       s->n_local = n_new;
+      lap("migrate");
+      mark("migrated", s->stream);
       if (s->n_local > 0) {
         NB_TRY(bh_build(s->tree, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local, s->d_box,
                         s->stream, &launches));
@@ -296,14 +325,51 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
         std::swap(s->d_ids, s->d_ids2);   std::swap(s->cap_ids, s->cap_ids2);
       }
       s->ids_identity = false;
-      if (ev) NB_CUDA(cudaEventRecord(ev[1], s->stream));
-      NB_TRY(bh_let_exchange(s->tree, s->tree_let, s->comm, bp, s->d_posm, (int)s->n_local, s->d_box, &s->n_let, s->stream, &launches));
-      if (ev) NB_CUDA(cudaEventRecord(ev[5], s->stream));   // [1]..[5] = LET exchange, reported as comm
-      if (s->n_local > 0) {
+      lap("local build");
+      mark("built", s->stream);
+      if (ev) { NB_CUDA(cudaEventRecord(ev[1], s->stream)); NB_CUDA(cudaEventRecord(ev[5], s->stream)); }
+      // The local walk (stream) and the LET exchange + LET tree build (stream_x, incl. its host synchronisation for the
+      // list sizes) are independent: run them side by side; the walk of the received points waits for both.
+      if (!s->stream_x) {
+        int lo = 0, hi = 0;
+        NB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        NB_CUDA(cudaStreamCreateWithPriority(&s->stream_x, cudaStreamNonBlocking, hi));
+        NB_CUDA(cudaEventCreateWithFlags(&s->ev_built, cudaEventDisableTiming));
+        NB_CUDA(cudaEventCreateWithFlags(&s->ev_let, cudaEventDisableTiming));
+      }
+      const bool overlap = !trace && getenv("NBODY_LET_NO_OVERLAP") == nullptr;
+      cudaStream_t sx = overlap ? s->stream_x : s->stream;
+      if (overlap) {
+        NB_CUDA(cudaEventRecord(s->ev_built, s->stream));
+        NB_CUDA(cudaStreamWaitEvent(sx, s->ev_built, 0));
+        bp.leave_sm_slot = true;
+        if (s->n_local > 0) NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
+        mark("local walk done", s->stream);
+        mark("x: start", sx);
+      }
+      NB_TRY(bh_let_exchange(s->tree, s->tree_let, s->comm, bp, s->d_posm, (int)s->n_local, s->d_box, &s->n_let, sx, &launches));
+      lap("let exchange");
+      mark("x: exchanged + let tree", sx);
+      if (overlap) {
+        NB_CUDA(cudaEventRecord(s->ev_let, sx));
+        NB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_let, 0));
+      } else if (s->n_local > 0) {
         NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
-        if (s->n_let > 0)
-          NB_TRY(bh_forces_from(s->tree_let, s->tree, bp, bh_let_sources(s->tree), s->d_posm, s->d_acc, s->n_let, 0, (int)s->n_local,
-                                true, s->stream, &launches));
+        lap("walk local");
+      }
+      bp.leave_sm_slot = false;
+      if (s->n_local > 0 && s->n_let > 0)
+        NB_TRY(bh_forces_from(s->tree_let, s->tree, bp, bh_let_sources(s->tree), s->d_posm, s->d_acc, s->n_let, 0, (int)s->n_local,
+                              true, s->stream, &launches));
+      lap("walk let");
+      mark("let walk done", s->stream);
+      if (evtrace) {
+        cudaStreamSynchronize(s->stream);
+        for (size_t k = 1; k < marks.size(); k++) {
+          float ms = 0; cudaEventElapsedTime(&ms, marks[0].second, marks[k].second);
+          fprintf(stderr, "[let-ev rank %d step %lld] %-26s @ %8.3f ms\n", s->cfg.rank, (long long)s->steps, marks[k].first, ms);
+        }
+        for (auto& mk : marks) cudaEventDestroy(mk.second);
       }
       s->launches += launches;
       if (ev) NB_CUDA(cudaEventRecord(ev[2], s->stream));
@@ -500,6 +566,9 @@ void nbody_destroy(nbody_sim* s) {
   for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream_x) cudaStreamDestroy(s->stream_x);
+  if (s->ev_built) cudaEventDestroy(s->ev_built);
+  if (s->ev_let) cudaEventDestroy(s->ev_let);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }

@@ -9,6 +9,8 @@
 // __match_any_sync (lane order == memory order), warp counts are prefixed across the CTA's warps, and each key goes to
 // base[digit] + rank. All HBM-bound: per pass 8 B key read (hist) + 12 B read + 12 B write (scatter) per body.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nbody {
@@ -169,17 +171,18 @@ struct RadixSortBuffers {
   uint32_t* tile_sums = nullptr;  // ceil(256 * nblocks / kScanTile)
 };
 
-// Sorts keys[0] (payload = iota) over `key_bits` low bits; the result is in keys[out], idx[out] (returned index).
-inline int radix_sort_pairs(RadixSortBuffers& b, int n, int key_bits, cudaStream_t s, double* launches) {
+// Sorts keys[0] (payload = iota) by bits [first_bit rounded down to a multiple of 8, key_bits); the result is in
+// keys[out], idx[out] (returned index). Lower bits keep their input order (stable).
+inline int radix_sort_pairs(RadixSortBuffers& b, int n, int key_bits, cudaStream_t s, double* launches, int first_bit = 0) {
   const int nblocks = (int)ceil_div(n, kSortTile);
   int cur = 0;
-  const int passes = (key_bits + 7) / 8;
-  for (int p = 0; p < passes; p++) {
+  const int passes = (key_bits + 7) / 8, p0 = std::max(0, std::min(first_bit / 8, passes - 1));
+  for (int p = p0; p < passes; p++) {
     const int shift = 8 * p;
     radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(b.keys[cur], n, shift, b.hist, nblocks);
     if (launches) *launches += 1;
     exclusive_scan_u32(b.hist, (int64_t)256 * nblocks, b.tile_sums, s, launches);
-    radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(b.keys[cur], p == 0 ? nullptr : b.idx[cur], n, shift, b.hist, nblocks,
+    radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(b.keys[cur], p == p0 ? nullptr : b.idx[cur], n, shift, b.hist, nblocks,
                                                            b.keys[cur ^ 1], b.idx[cur ^ 1]);
     if (launches) *launches += 1;
     cur ^= 1;
