@@ -169,7 +169,7 @@ def workload_config(args, wl, world):
             "partition": ("1 GPU" if world == 1 else
                           f"i-rows over {world} GPUs, NCCL all-gather of float4 positions per step" if method == "direct" else
                           f"Morton domain split over {world} GPUs, body migration + locally-essential-tree exchange (NCCL all-to-all-v)"
-                          if getattr(args, "bh_exchange", 0) == 0 else
+                          if (getattr(args, "bh_exchange", -1) == 0 or (getattr(args, "bh_exchange", -1) < 0 and n > (1 << 25))) else
                           f"replicated tree, Morton-order slices over {world} GPUs, all-gather of positions + velocities"),
             "l2": "flushed between timed steps (256 MiB memset); sources (16 B/body) are re-read from L2 by design",
             "seed": 1234}
@@ -357,7 +357,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="plummer_1m_direct", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--bh-exchange", type=int, default=0, choices=[0, 1],
+    ap.add_argument("--bh-exchange", type=int, default=-1, choices=[-1, 0, 1],
                     help="multi-GPU Barnes-Hut: 0 = Morton domain split + LET exchange, 1 = replicated tree")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

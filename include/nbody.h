@@ -76,7 +76,8 @@ typedef struct nbody_config {
                              groups (default 2; larger = fuller lanes, looser group boxes) */
   int32_t bh_exchange;    /* multi-GPU Barnes-Hut: 0 = Morton domain split, body migration and locally-essential-tree exchange
                              (each rank holds only its domain); 1 = replicated tree (every rank holds all bodies, walks its
-                             slice of the Morton order, all-gathers positions and velocities) */
+                             slice of the Morton order, all-gathers positions and velocities); -1 (default) = by size:
+                             replicated up to 2^25 bodies, domain split above */
   int32_t reserved[1];
   uint8_t nccl_unique_id[128]; /* multi-GPU: the ncclUniqueId from nbody_comm_unique_id on rank 0. All zeros with world > 1 =
                                   an EMULATED rank: no communicator; the handle evaluates its slice of the bodies given by
@@ -194,6 +195,13 @@ int nbody_device_ptrs(nbody_sim* sim, void** posm4, void** vel4, void** acc4);
  * Morton keys (3 bits per level, 4*X + 2*Y + Z as Octree::GetOctant, h:50-56). Any output pointer may be NULL. */
 int nbody_octree_nodes(nbody_sim* sim, float* com4, int32_t* meta4, int32_t* range2, uint64_t* keys, int64_t cap_nodes,
                        int64_t cap_keys, int64_t* n_nodes);
+
+/* Checkpoint / resume (no counterpart in the reference): a flat little-endian file - 80-byte header
+ * (magic "NBODYB2", version, n, steps, G, eps, theta, PhDeltaTime, method) + posm float4[n] + vel float4[n] in the caller's
+ * original body order. Loading sets the bodies (all ranks read the same file and keep their share), restores the
+ * parameters and the step count; the handle's method is kept. Saving needs a single-rank handle. */
+int nbody_save_snapshot(nbody_sim* sim, const char* path);
+int nbody_load_snapshot(nbody_sim* sim, const char* path);
 
 /* ---- multi-GPU plumbing --------------------------------------------------------------------------- */
 /* 128-byte ncclUniqueId; rank 0 creates it and the launcher broadcasts it to all ranks before nbody_create. */

@@ -65,7 +65,7 @@ EXPORTS = [
     "nbody_synchronize", "nbody_get_particles_aos", "nbody_get_positions", "nbody_get_velocities",
     "nbody_get_accelerations", "nbody_get_local_ids", "nbody_set_param", "nbody_get_param", "nbody_energy",
     "nbody_stats_get", "nbody_octree_boxes", "nbody_device_ptrs", "nbody_comm_unique_id", "nbody_measure_fp32_peak",
-    "nbody_octree_nodes", "nbody_sort_pairs_u64",
+    "nbody_octree_nodes", "nbody_sort_pairs_u64", "nbody_save_snapshot", "nbody_load_snapshot",
 ]
 
 _lib = None
@@ -113,6 +113,8 @@ def load_library():
     L.nbody_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.nbody_comm_unique_id.argtypes = [vp]
     L.nbody_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.nbody_save_snapshot.argtypes = [vp, C.c_char_p]
+    L.nbody_load_snapshot.argtypes = [vp, C.c_char_p]
     L.nbody_octree_nodes.argtypes = [vp, vp, vp, vp, vp, i64, i64, C.POINTER(i64)]
     L.nbody_sort_pairs_u64.argtypes = [C.c_int32, vp, i64, C.c_int32, vp, vp, C.POINTER(C.c_float)]
     if L.nbody_abi_version() != 1:
@@ -165,7 +167,7 @@ class OctreeSearch:
     def __init__(self, method: int = METHOD_BARNES_HUT, G: float = 1e4, eps: float = 0.0, theta: float = 1.0,
                  PhDeltaTime: float = 0.01, device: int = 0, rank: int = 0, world: int = 1,
                  nccl_unique_id: bytes | None = None, leaf_size: int = 16, reference_root: bool = False,
-                 mac: int = 0, group_size: int = 64, group_pack: int = 2, bh_exchange: int = 0, stream: int | None = None):
+                 mac: int = 0, group_size: int = 64, group_pack: int = 2, bh_exchange: int = -1, stream: int | None = None):
         self._L = load_library()
         cfg = _Config()
         _check(self._L.nbody_config_default(C.byref(cfg)))
@@ -295,6 +297,12 @@ class OctreeSearch:
         out = np.zeros((cap, 7), np.float32)
         _check(self._L.nbody_octree_boxes(self._h, _ptr(out), cap, C.byref(n)))
         return out[:n.value]
+
+    def SaveSnapshot(self, path: str):
+        _check(self._L.nbody_save_snapshot(self._h, os.fsencode(path)))
+
+    def LoadSnapshot(self, path: str):
+        _check(self._L.nbody_load_snapshot(self._h, os.fsencode(path)))
 
     def OctreeNodes(self) -> dict:
         """The last Barnes-Hut build: per-node centre of mass + mass, (first, count, level | 256*leaf, parent), body range,

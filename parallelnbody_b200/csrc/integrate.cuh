@@ -116,14 +116,14 @@ aos_to_soa_kernel(const uint8_t* __restrict__ aos, const size_t stride, const in
   vel[i] = make_float4(r[4], r[5], r[6], 0.f);
   acc[i] = make_float4(r[7], r[8], r[9], 0.f);
 }
-// Writes local body i into record i of a compact staging array (n records of 40 B).
+// Writes local body i into record i (ids == nullptr) or record ids[i] of a compact staging array (n records of 40 B).
 __global__ void __launch_bounds__(256)
 soa_to_aos_kernel(const float4* __restrict__ posm, const float4* __restrict__ vel, const float4* __restrict__ acc,
-                  const int n, float* __restrict__ aos10) {
+                  const int n, const int32_t* __restrict__ ids, float* __restrict__ aos10) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = posm[i], v = vel[i], a = acc[i];
-  float* r = aos10 + (size_t)i * 10;
+  float* r = aos10 + (size_t)(ids ? ids[i] : i) * 10;
   r[0] = p.w; r[1] = p.x; r[2] = p.y; r[3] = p.z; r[4] = v.x; r[5] = v.y; r[6] = v.z; r[7] = a.x; r[8] = a.y; r[9] = a.z;
 }
 
@@ -212,6 +212,13 @@ energy_kernel(const float4* __restrict__ src, const int n_src, const float4* __r
     atomicAdd(out, ke);
     atomicAdd(out + 1, pe);
   }
+}
+
+// out[ids[i]] = in[i]: undoes the Morton reordering for a read-back.
+__global__ void __launch_bounds__(256)
+scatter_float4_kernel(const float4* __restrict__ in, const int32_t* __restrict__ ids, const int n, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[ids[i]] = in[i];
 }
 
 __global__ void fill_float4_kernel(float4* p, const int64_t n, const float4 v) {

@@ -4,10 +4,10 @@
 // octree (Octree::Add, /root/reference/Source/NBody/OctreeSearch.h:60-81): sorting the bodies along the Morton curve
 // makes every octree cell a contiguous index range.
 //
-// 8 passes of 8 bits. Per pass: (1) per-CTA digit histogram, (2) exclusive scan of the digit-major table
-// hist[digit][cta] (gives every CTA its global base per digit), (3) stable scatter: each warp ranks its keys with
-// __match_any_sync (lane order == memory order), warp counts are prefixed across the CTA's warps, and each key goes to
-// base[digit] + rank. All HBM-bound: per pass 8 B key read (hist) + 12 B read + 12 B write (scatter) per body.
+// 8 passes of 8 bits (fewer when the tree needs fewer levels). Per pass: (1) per-CTA digit histogram, (2) exclusive scan
+// of the digit-major table hist[digit][cta] (gives every CTA its global base per digit), (3) stable scatter of 4096-key
+// tiles staged in shared memory (see radix_scatter_kernel). All HBM-bound: per pass 8 B key read (hist) + 12 B read +
+// 12 B write (scatter) per body.
 #pragma once
 #include <algorithm>
 
@@ -16,8 +16,8 @@
 namespace nbody {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 8;                               // keys per thread
-constexpr int kSortTile = kSortThreads * kSortItems;        // 2048 keys per CTA
+constexpr int kSortItems = 16;                              // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;        // 4096 keys per CTA
 constexpr int kSortWarps = kSortThreads / 32;
 
 // ---- exclusive scan of uint32 (three small kernels; n up to 2^31) --------------------------------------------
@@ -114,18 +114,28 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, const int n, const int shif
   hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// hist must already hold the exclusive scan of the digit-major table. idx_in == nullptr: payload = position (pass 0).
+// hist must already hold the exclusive scan of the digit-major table. idx_in == nullptr: payload = position (first pass).
+// Stable scatter in three steps: (1) every warp ranks its 512 keys among equal digits with warp ballots (round r,
+// lane l = memory order); (2) warp counts are prefixed over the CTA's warps and digit totals over the digits, which
+// gives each key its position in the CTA's sorted tile - the tile is staged in shared memory in that order; (3) the
+// staged tile is written out front to back, so consecutive threads write consecutive addresses within each digit run.
+constexpr int kSortSmemBytes = kSortTile * 12 + (kSortWarps * 256 + 3 * 256) * 4;
+
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, const int n,
                      const int shift, const uint32_t* __restrict__ hist, const int nblocks,
                      uint64_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
-  __shared__ uint32_t wcount[kSortWarps][256];
-  __shared__ uint32_t dbase[256];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* skey = reinterpret_cast<uint64_t*>(smem_raw);                       // [kSortTile]
+  uint32_t* sidx = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSortTile * 8);   // [kSortTile]
+  uint32_t* wcount = sidx + kSortTile;                                          // [kSortWarps][256]
+  uint32_t* dbase = wcount + kSortWarps * 256;                                  // [256] global base of digit d for this CTA
+  uint32_t* lbase = dbase + 256;                                                // [256] start of digit d inside the sorted tile
+  uint32_t* dtot = lbase + 256;                                                 // [256]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < kSortWarps; k++) wcount[k][threadIdx.x] = 0;
+  for (int k = 0; k < kSortWarps; k++) wcount[k * 256 + threadIdx.x] = 0;
   __syncthreads();
-  // warp w owns the contiguous segment [seg, seg + 32 * kSortItems); round r, lane l -> seg + 32 r + l
   const int seg = blockIdx.x * kSortTile + w * (32 * kSortItems);
   uint64_t key[kSortItems];
   uint32_t rank[kSortItems];
@@ -134,33 +144,54 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
     const int i = seg + 32 * r + lane;
     const bool live = i < n;
     key[r] = live ? keys_in[i] : ~0ull;
-    const uint32_t d = live ? ((uint32_t)(key[r] >> shift) & 255u) : 0xffffffffu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t d = live ? ((uint32_t)(key[r] >> shift) & 255u) : 0u;
+    // lanes holding the same digit: 8 ballots (one per digit bit) + 1 for liveness; much cheaper than MATCH.ANY on ~30
+    // distinct values per warp
+    uint32_t peers = __ballot_sync(0xffffffffu, live);
+    if (!live) peers = ~peers;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+      peers &= ((d >> b) & 1u) ? bal : ~bal;
+    }
     const uint32_t before = __popc(peers & ((1u << lane) - 1u));
     uint32_t prev = 0;
-    if (live) prev = wcount[w][d];
+    if (live) prev = wcount[w * 256 + d];
     __syncwarp();
-    if (live && before == 0) wcount[w][d] = prev + __popc(peers);
+    if (live && before == 0) wcount[w * 256 + d] = prev + __popc(peers);
     __syncwarp();
     rank[r] = prev + before;
   }
   __syncthreads();
+  uint32_t total_d;
   {  // thread d: prefix the warp counts of digit d over the CTA's warps, fetch the global base
     uint32_t run = 0;
 #pragma unroll
-    for (int k = 0; k < kSortWarps; k++) { const uint32_t t = wcount[k][threadIdx.x]; wcount[k][threadIdx.x] = run; run += t; }
+    for (int k = 0; k < kSortWarps; k++) { const uint32_t t = wcount[k * 256 + threadIdx.x]; wcount[k * 256 + threadIdx.x] = run; run += t; }
+    total_d = run;
+    dtot[threadIdx.x] = run;
     dbase[threadIdx.x] = hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
   }
+  uint32_t tile_total;
+  lbase[threadIdx.x] = block_excl_scan(total_d, &tile_total);
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kSortItems; r++) {
     const int i = seg + 32 * r + lane;
     if (i < n) {
       const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
-      const uint32_t pos = dbase[d] + wcount[w][d] + rank[r];
-      keys_out[pos] = key[r];
-      idx_out[pos] = idx_in ? idx_in[i] : (uint32_t)i;
+      const uint32_t lpos = lbase[d] + wcount[w * 256 + d] + rank[r];
+      skey[lpos] = key[r];
+      sidx[lpos] = idx_in ? idx_in[i] : (uint32_t)i;
     }
+  }
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < tile_total; j += kSortThreads) {
+    const uint64_t k = skey[j];
+    const uint32_t d = (uint32_t)(k >> shift) & 255u;
+    const uint32_t pos = dbase[d] + (j - lbase[d]);
+    keys_out[pos] = k;
+    idx_out[pos] = sidx[j];
   }
 }
 
@@ -175,6 +206,8 @@ struct RadixSortBuffers {
 // keys[out], idx[out] (returned index). Lower bits keep their input order (stable).
 inline int radix_sort_pairs(RadixSortBuffers& b, int n, int key_bits, cudaStream_t s, double* launches, int first_bit = 0) {
   const int nblocks = (int)ceil_div(n, kSortTile);
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemBytes);
+  (void)attr_rc;
   int cur = 0;
   const int passes = (key_bits + 7) / 8, p0 = std::max(0, std::min(first_bit / 8, passes - 1));
   for (int p = p0; p < passes; p++) {
@@ -182,7 +215,7 @@ inline int radix_sort_pairs(RadixSortBuffers& b, int n, int key_bits, cudaStream
     radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(b.keys[cur], n, shift, b.hist, nblocks);
     if (launches) *launches += 1;
     exclusive_scan_u32(b.hist, (int64_t)256 * nblocks, b.tile_sums, s, launches);
-    radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(b.keys[cur], p == p0 ? nullptr : b.idx[cur], n, shift, b.hist, nblocks,
+    radix_scatter_kernel<<<nblocks, kSortThreads, kSortSmemBytes, s>>>(b.keys[cur], p == p0 ? nullptr : b.idx[cur], n, shift, b.hist, nblocks,
                                                            b.keys[cur ^ 1], b.idx[cur ^ 1]);
     if (launches) *launches += 1;
     cur ^= 1;

@@ -5,15 +5,15 @@ import numpy as np
 import parallelnbody_b200 as P
 from parallelnbody_b200 import ic
 
-sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1 << 20, 1 << 22]
+sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1 << 20, 1 << 22, 1 << 24]
 for n in sizes:
     posm, vel = ic.plummer(n, seed=1234)
     keys = np.random.default_rng(1).integers(0, 1 << 63, n, dtype=np.uint64)
     _, _, ms = P.sort_pairs_u64(keys, 63, timed=True)
     print(f"N={n}: radix sort 63-bit pairs {ms:.3f} ms = {n / ms * 1e-6:.2f} Gkeys/s")
     for th in (0.25, 0.35):
-        for gs in (64, 128):
-            for pack in (1, 2, 4, 8, 16):
+        for gs in (64,):
+            for pack in (2,):
                 leaf = 16
                 with P.OctreeSearch(method=P.METHOD_BARNES_HUT, eps=0.01, theta=th, leaf_size=leaf, group_size=gs, group_pack=pack) as s:
                     s.SetBodies(posm, vel)
