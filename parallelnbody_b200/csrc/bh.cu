@@ -34,6 +34,7 @@ constexpr int kBodyFlag = 1 << 30;       // walk-stack entry is a body index, no
 // walk groups hold <= group_size bodies (32 * B, B bodies per lane, B in {1, 2, 4})
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
+constexpr int kWalkMinCtas = 3;          // register budget: 85 per thread -> 24 warps per SM (64 regs / 4 CTAs measured no faster)
 constexpr int kStackCap = 8192;          // per-warp walk stack entries (HBM/L2 resident)
 constexpr int kListCap = 64;             // per-warp interaction ring in shared memory
 constexpr int kLetSamples = 256;         // key samples per rank for the domain splitters
@@ -383,7 +384,7 @@ __device__ __forceinline__ void eval_list(const float* __restrict__ ring, const 
 }
 
 template <int B, bool EPS0>
-__global__ void __launch_bounds__(kWalkThreads)
+__global__ void __launch_bounds__(kWalkThreads, B <= 2 ? kWalkMinCtas : 2)
 bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com, const int4* __restrict__ node_meta,
                      const float4* __restrict__ tgt, const int2* __restrict__ groups, Counters* __restrict__ c,
                      const float4* __restrict__ root, const float theta2, const float eps2, const float G, const int t0,
