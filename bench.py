@@ -307,8 +307,12 @@ def run_ours(args, wl):
         value = pairs_all / (ms_total_max * 1e-3)
         e2e_value = float(n) * float(n) * e2e_steps / e2e_s
         ach = FLOPS_PER_INTERACTION * local_pairs * args.steps / (ms_force * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed ncu --set full capture of this
+        # workload (profiles/r1_direct_kernel_ncu_summary.md): 40.2 MB read + 223.4 MB written, against 16.8 MB of sources
+        # + 268 MB of j-split partials; irrelevant to the bound (0.6 GB/s-class traffic in a 413 ms kernel)
+        traffic = 263.66e6 if (args.workload == "plummer_1m_direct" and world == 1) else None
         roof = {"bound": "fp32", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "peak_kind": f"measured FFMA-chain burst on this GPU ({peak_mhz:.0f} MHz); MEASURED_PEAKS.json has no FP32 entry",
+                "traffic": traffic, "peak_kind": f"measured FFMA-chain burst on this GPU ({peak_mhz:.0f} MHz); MEASURED_PEAKS.json has no FP32 entry",
                 "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_nominal": ach / FP32_NOMINAL_TFLOPS,
                 "kernel": "direct_packed_kernel", "flops_per_interaction": FLOPS_PER_INTERACTION,
                 "ms_per_launch": ms_force / args.steps}
@@ -318,7 +322,7 @@ def run_ours(args, wl):
         e2e_value = e2e_steps / e2e_s
         ach = FLOPS_PER_INTERACTION * interactions / (ms_force * 1e-3) / 1e12
         roof = {"bound": "fp32", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "kernel": "bh_walk_kernel", "interactions_per_step": inter_all / args.steps,
+                "traffic": None, "kernel": "bh_walk_group_kernel", "interactions_per_step": inter_all / args.steps,
                 "ms_per_launch": ms_force / args.steps, "ms_build_per_step": ms_build / args.steps}
 
     if rank != 0:

@@ -254,8 +254,26 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
       continue;
     }
     const int shift = 3 * (kMaxLevel - 1 - level);
+    // first body whose digit at this level is >= sub: 8-ary search (7 independent probes per round, so the chain of
+    // dependent L2 round trips is log8 of the range), then a binary search on the last few bodies
     int lo = r.x, hi = r.y;
-    while (lo < hi) {  // first body whose digit at this level is >= sub
+    while (hi - lo > 16) {
+      const int w = (hi - lo) >> 3;
+      int d[7];
+#pragma unroll
+      for (int k = 0; k < 7; k++) d[k] = (int)((keys[lo + (k + 1) * w] >> shift) & 7ull);
+      int nlo = lo, nhi = hi;
+      bool found = false;
+#pragma unroll
+      for (int k = 0; k < 7; k++) {
+        if (!found) {
+          if (d[k] >= sub) { nhi = lo + (k + 1) * w; found = true; }
+          else nlo = lo + (k + 1) * w + 1;
+        }
+      }
+      lo = nlo; hi = nhi;
+    }
+    while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if ((int)((keys[mid] >> shift) & 7ull) < sub) lo = mid + 1; else hi = mid;
     }
