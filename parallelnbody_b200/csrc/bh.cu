@@ -689,10 +689,16 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
   {
     int leaf = std::max(1, p.leaf_size), gs = p.group_size, sup = super, lv = levels;
     void* args[] = {(void*)&keys, &leaf, &gs, &sup, &lv, &m->node_range, &m->node_meta, &m->node_ready, &m->groups, &m->counters};
-    // co-resident by construction: at most 2 CTAs per SM (1 when another stream's walk shares the SMs)
-    NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(kNumSMsB200 * (p.leave_sm_slot ? 1 : 2)), dim3(256), args, 0, s));
+    // as many CTAs as are co-resident (the split is latency bound: dependent key probes), 1 per SM when another
+    // stream's walk shares the SMs
+    static int split_ctas = 0;
+    if (!split_ctas) {
+      NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split_ctas, tree_split_kernel, 256, 0));
+      split_ctas = std::max(1, std::min(split_ctas, 8));
+    }
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(kNumSMsB200 * (p.leave_sm_slot ? 1 : split_ctas)), dim3(256), args, 0, s));
   }
-  monopole_kernel<<<kNumSMsB200 * 4, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
+  monopole_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
   *launches += 2;
   NB_CUDA(cudaGetLastError());
   return 0;

@@ -105,10 +105,16 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, const int n, const int shif
   h[threadIdx.x] = 0;
   __syncthreads();
   const int base = blockIdx.x * kSortTile;
+  uint64_t key[kSortItems];
 #pragma unroll
   for (int k = 0; k < kSortItems; k++) {
     const int i = base + k * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    key[k] = i < n ? keys[i] : 0ull;
+  }
+#pragma unroll
+  for (int k = 0; k < kSortItems; k++) {
+    const int i = base + k * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(uint32_t)(key[k] >> shift) & 255u], 1u);
   }
   __syncthreads();
   hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
@@ -139,11 +145,16 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
   const int seg = blockIdx.x * kSortTile + w * (32 * kSortItems);
   uint64_t key[kSortItems];
   uint32_t rank[kSortItems];
+  // all 16 loads first (independent, one memory round trip), then the ranking rounds, which synchronise the warp
+#pragma unroll
+  for (int r = 0; r < kSortItems; r++) {
+    const int i = seg + 32 * r + lane;
+    key[r] = i < n ? keys_in[i] : ~0ull;
+  }
 #pragma unroll
   for (int r = 0; r < kSortItems; r++) {
     const int i = seg + 32 * r + lane;
     const bool live = i < n;
-    key[r] = live ? keys_in[i] : ~0ull;
     const uint32_t d = live ? ((uint32_t)(key[r] >> shift) & 255u) : 0u;
     // lanes holding the same digit: 8 ballots (one per digit bit) + 1 for liveness; much cheaper than MATCH.ANY on ~30
     // distinct values per warp
@@ -175,6 +186,12 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
   uint32_t tile_total;
   lbase[threadIdx.x] = block_excl_scan(total_d, &tile_total);
   __syncthreads();
+  uint32_t pay[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; r++) {
+    const int i = seg + 32 * r + lane;
+    pay[r] = (idx_in && i < n) ? idx_in[i] : (uint32_t)i;
+  }
 #pragma unroll
   for (int r = 0; r < kSortItems; r++) {
     const int i = seg + 32 * r + lane;
@@ -182,7 +199,7 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
       const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
       const uint32_t lpos = lbase[d] + wcount[w * 256 + d] + rank[r];
       skey[lpos] = key[r];
-      sidx[lpos] = idx_in ? idx_in[i] : (uint32_t)i;
+      sidx[lpos] = pay[r];
     }
   }
   __syncthreads();
