@@ -34,7 +34,8 @@ constexpr int kBodyFlag = 1 << 30;       // walk-stack entry is a body index, no
 // walk groups hold <= group_size bodies (32 * B, B bodies per lane, B in {1, 2, 4})
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
-constexpr int kWalkMinCtas = 3;          // register budget: 85 per thread -> 24 warps per SM (64 regs / 4 CTAs measured no faster)
+constexpr int kWalkMinCtas = 4;          // register budget: 64 per thread -> 32 warps per SM; measured equal to 80 regs x 3 CTAs, and it leaves
+                                         // room for another stream's small kernels when the LET exchange runs beside a 3-CTA walk
 constexpr int kStackCap = 8192;          // per-warp walk stack entries (HBM/L2 resident)
 constexpr int kListCap = 64;             // per-warp interaction ring in shared memory
 constexpr int kLetSamples = 256;         // key samples per rank for the domain splitters
@@ -785,7 +786,8 @@ int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t
 // K9 - multi-GPU Barnes-Hut: Morton domain split, body migration and locally-essential-tree (LET) exchange.
 //
 // Every rank owns a contiguous range of the GLOBAL Morton order (keys are taken in one root cube shared by all ranks).
-// Per step:  (1) keys of the local bodies, regular key samples -> all-gather -> W-1 splitters (equal-count quantiles);
+// Per step:  (1) keys of the local bodies, regular key samples -> all-gather -> W-1 splitters (equal-WORK quantiles: a
+//                rank's samples are weighted by its body count and the time its walks took last step);
 //            (2) bodies are bucketed by destination rank (one 8-bit radix pass) and exchanged (all-to-all-v);
 //            (3) the local tree is built over the bodies now owned;
 //            (4) each rank publishes the bounding boxes of kLetBoxes cells of its local tree (a cut below the root); for every peer the local tree is
@@ -799,20 +801,56 @@ int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t
 // =====================================================================================================================
 namespace {
 
-__global__ void let_sample_kernel(const uint64_t* __restrict__ keys, const int n, uint64_t* __restrict__ out) {
+// A rank's message to the splitter selection: kLetSamples keys at regular positions of its (nearly Morton-sorted) bodies
+// + its body count + the device time its walks took last step (0 = unknown).
+constexpr int kLetMsg = kLetSamples + 2;
+
+__global__ void let_sample_kernel(const uint64_t* __restrict__ keys, const int n, const float walk_ms, uint64_t* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kLetSamples) return;
-  out[i] = n > 0 ? keys[(int)(((long long)i * n + n / 2) / kLetSamples) < n ? (int)(((long long)i * n + n / 2) / kLetSamples) : n - 1] : ~0ull;
+  if (i < kLetSamples) {
+    const int j = min((int)(((long long)i * n + n / 2) / kLetSamples), n - 1);
+    out[i] = n > 0 ? keys[j] : ~0ull;
+  } else if (i == kLetSamples) {
+    out[i] = (uint64_t)n;
+  } else if (i == kLetSamples + 1) {
+    out[i] = (uint64_t)__float_as_uint(walk_ms);
+  }
 }
 
-// One CTA: sort the world * kLetSamples gathered samples (bitonic, shared memory) and take the equal-count quantiles.
+// One CTA: sort the gathered samples by key (bitonic, shared memory) and cut them into `world` pieces of equal WEIGHT.
+// A sample of rank q stands for 1/kLetSamples of that rank's cost = a blend of its share of the bodies and its share
+// of last step's walk time (equal work, not just equal counts: dense regions cost more interactions per body).
 __global__ void __launch_bounds__(1024)
-let_splitters_kernel(const uint64_t* __restrict__ samples, const int world, uint64_t* __restrict__ splitters) {
-  extern __shared__ uint64_t sk[];
+let_splitters_kernel(const uint64_t* __restrict__ msgs, const int world, uint64_t* __restrict__ splitters) {
+  extern __shared__ uint64_t sk[];                 // [pow2] keys, then [pow2] floats (weights -> inclusive prefix)
   const int total = world * kLetSamples;
   int pow2 = 1;
   while (pow2 < total) pow2 <<= 1;
-  for (int i = threadIdx.x; i < pow2; i += blockDim.x) sk[i] = i < total ? samples[i] : ~0ull;
+  float* sw = reinterpret_cast<float*>(sk + pow2);
+  __shared__ float wq[kMaxWorld];
+  if (threadIdx.x == 0) {
+    double sum_n = 0, sum_t = 0;
+    bool timed = true;
+    for (int q = 0; q < world; q++) {
+      const double nq = (double)msgs[(size_t)q * kLetMsg + kLetSamples];
+      const float tq = __uint_as_float((uint32_t)msgs[(size_t)q * kLetMsg + kLetSamples + 1]);
+      sum_n += nq; sum_t += tq;
+      if (nq > 0 && !(tq > 0.f)) timed = false;      // some rank has no timing yet: fall back to counts
+    }
+    for (int q = 0; q < world; q++) {
+      const double nq = (double)msgs[(size_t)q * kLetMsg + kLetSamples];
+      const float tq = __uint_as_float((uint32_t)msgs[(size_t)q * kLetMsg + kLetSamples + 1]);
+      double w = sum_n > 0 ? nq / sum_n : 1.0 / world;
+      if (timed && sum_t > 0) w = 0.3 * w + 0.7 * (double)tq / sum_t;
+      wq[q] = (float)(w / kLetSamples);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < pow2; i += blockDim.x) {
+    const int q = i / kLetSamples;
+    sk[i] = i < total ? msgs[(size_t)q * kLetMsg + (i % kLetSamples)] : ~0ull;
+    sw[i] = i < total ? wq[q] : 0.f;
+  }
   __syncthreads();
   for (int k = 2; k <= pow2; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -821,12 +859,29 @@ let_splitters_kernel(const uint64_t* __restrict__ samples, const int world, uint
         if (l > i) {
           const uint64_t a = sk[i], b = sk[l];
           const bool up = (i & k) == 0;
-          if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+          if ((a > b) == up) { sk[i] = b; sk[l] = a; const float t = sw[i]; sw[i] = sw[l]; sw[l] = t; }
         }
       }
       __syncthreads();
     }
-  for (int r = threadIdx.x + 1; r < world; r += blockDim.x) splitters[r - 1] = sk[r * kLetSamples];
+  // inclusive prefix of the weights (Hillis-Steele; pow2 <= 4096 elements, 1024 threads)
+  for (int off = 1; off < pow2; off <<= 1) {
+    float v[4];
+    int cnt = 0;
+    for (int i = threadIdx.x; i < pow2; i += blockDim.x) v[cnt++] = i >= off ? sw[i - off] : 0.f;
+    __syncthreads();
+    cnt = 0;
+    for (int i = threadIdx.x; i < pow2; i += blockDim.x) sw[i] += v[cnt++];
+    __syncthreads();
+  }
+  const float all = sw[pow2 - 1];
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const float hi = sw[i], lo = i ? sw[i - 1] : 0.f;
+    for (int r = 1; r < world; r++) {
+      const float target = all * (float)r / (float)world;
+      if (lo < target && target <= hi) splitters[r - 1] = sk[i];
+    }
+  }
 }
 
 // keys[i] <- destination rank of body i = number of splitters <= key (bodies with equal keys stay together).
@@ -951,7 +1006,7 @@ let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ no
 int let_ensure(Impl* m, int world, int64_t cap_local, cudaStream_t s) {
   if (m->let_world != world) {
     NB_CUDA(cudaStreamSynchronize(s));
-    NB_TRY(realloc_dev(&m->samples, (size_t)(world + 1) * kLetSamples));
+    NB_TRY(realloc_dev(&m->samples, (size_t)(world + 1) * kLetMsg));
     NB_TRY(realloc_dev(&m->splitters, (size_t)world));
     NB_TRY(realloc_dev(&m->send_off, (size_t)world + 1));
     NB_TRY(realloc_dev(&m->all_off, (size_t)world * (world + 1)));
@@ -973,7 +1028,7 @@ int let_ensure(Impl* m, int world, int64_t cap_local, cudaStream_t s) {
 // Phases (1)-(2): on return the first *n_local entries of posm_a / vel_a / ids_a hold the bodies this rank owns now
 // (`world` runs received from the peers, not yet sorted). posm_b / vel_b / ids_b are scratch (send staging).
 int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
-                   float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local,
+                   float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, float walk_ms, int* n_local,
                    cudaStream_t s, double* launches) {
   Impl* m = impl_of(st);
   const int world = comm->world(), rank = comm->rank();
@@ -983,11 +1038,11 @@ int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, f
   const unsigned nb = (unsigned)ceil_div(std::max(n, 1), 256);
   root_cube_kernel<<<1, 1, 0, s>>>(box_global, p.reference_root ? 1 : 0, m->root);
   if (n > 0) morton_kernel<<<nb, 256, 0, s>>>(posm_a, n, m->root, m->sort.keys[0]);
-  let_sample_kernel<<<1, kLetSamples, 0, s>>>(m->sort.keys[0], n, m->samples + (size_t)world * kLetSamples);
-  NB_TRY(comm->all_gather_bytes(m->samples + (size_t)world * kLetSamples, m->samples, (size_t)kLetSamples * 8, s));
+  let_sample_kernel<<<1, 288, 0, s>>>(m->sort.keys[0], n, walk_ms, m->samples + (size_t)world * kLetMsg);
+  NB_TRY(comm->all_gather_bytes(m->samples + (size_t)world * kLetMsg, m->samples, (size_t)kLetMsg * 8, s));
   int pow2 = 1;
   while (pow2 < world * kLetSamples) pow2 <<= 1;
-  let_splitters_kernel<<<1, 1024, (size_t)pow2 * 8, s>>>(m->samples, world, m->splitters);
+  let_splitters_kernel<<<1, 1024, (size_t)pow2 * 12, s>>>(m->samples, world, m->splitters);
   *launches += 4;
   int sorted = 0;
   if (n > 0) {

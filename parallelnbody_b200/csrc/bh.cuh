@@ -55,7 +55,7 @@ int bh_forces_from(BHState& src, BHState& tgt_tree, const BHParams& p, const flo
 // ---- multi-GPU (K9): Morton domain split + body migration + locally-essential-tree exchange; see bh.cu
 class Comm;
 int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
-                   float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local,
+                   float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, float walk_ms, int* n_local,
                    cudaStream_t s, double* launches);
 int bh_let_exchange(BHState& local, BHState& let, Comm* comm, const BHParams& p, const float4* posm, int n,
                     const uint32_t* box_global, int* n_let, cudaStream_t s, double* launches);

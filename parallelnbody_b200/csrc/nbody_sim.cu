@@ -82,6 +82,8 @@ struct nbody_sim {
   bool own_stream = false;
   cudaStream_t stream_x = nullptr;          // LET mode: exchange stream, runs beside the local walk
   cudaEvent_t ev_built = nullptr, ev_let = nullptr;
+  cudaEvent_t ev_walk[4] = {nullptr, nullptr, nullptr, nullptr};   // LET mode: around the local walk and the LET walk
+  bool walk_timed = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_pool;
 
@@ -315,8 +317,18 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       };
       mark("start(after cube)", s->stream);
       int n_new = 0;
+      // device time of last step's walks on this rank = the weight of its domain in the next split (equal work per rank)
+      float walk_ms = 0.f;
+      if (s->ev_walk[0] && s->walk_timed) {
+        float a = 0.f, b = 0.f;
+        cudaEventSynchronize(s->ev_walk[3]);   // last step's walks (the migration below synchronises anyway)
+        if (cudaEventElapsedTime(&a, s->ev_walk[0], s->ev_walk[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&b, s->ev_walk[2], s->ev_walk[3]) == cudaSuccess) walk_ms = a + b;
+        else cudaGetLastError();
+      }
       NB_TRY(bh_let_migrate(s->tree, s->comm, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local,
-                            std::min(s->cap_posm, s->cap_posm2), s->d_box, &n_new, s->stream, &launches));
+                            std::min(s->cap_posm, s->cap_posm2), s->d_box, walk_ms, &n_new, s->stream, &launches));
+      if (!s->ev_walk[0]) for (int q = 0; q < 4; q++) NB_CUDA(cudaEventCreate(&s->ev_walk[q]));
       s->n_local = n_new;
       lap("migrate");
       mark("migrated", s->stream);
@@ -346,7 +358,9 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
         NB_CUDA(cudaEventRecord(s->ev_built, s->stream));
         NB_CUDA(cudaStreamWaitEvent(sx, s->ev_built, 0));
         bp.leave_sm_slot = true;
+        NB_CUDA(cudaEventRecord(s->ev_walk[0], s->stream));
         if (s->n_local > 0) NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
+        NB_CUDA(cudaEventRecord(s->ev_walk[1], s->stream));
         mark("local walk done", s->stream);
         mark("x: start", sx);
       }
@@ -356,14 +370,19 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       if (overlap) {
         NB_CUDA(cudaEventRecord(s->ev_let, sx));
         NB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_let, 0));
-      } else if (s->n_local > 0) {
-        NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
+      } else {
+        NB_CUDA(cudaEventRecord(s->ev_walk[0], s->stream));
+        if (s->n_local > 0) NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
+        NB_CUDA(cudaEventRecord(s->ev_walk[1], s->stream));
         lap("walk local");
       }
       bp.leave_sm_slot = false;
+      NB_CUDA(cudaEventRecord(s->ev_walk[2], s->stream));
       if (s->n_local > 0 && s->n_let > 0)
         NB_TRY(bh_forces_from(s->tree_let, s->tree, bp, bh_let_sources(s->tree), s->d_posm, s->d_acc, s->n_let, 0, (int)s->n_local,
                               true, s->stream, &launches));
+      NB_CUDA(cudaEventRecord(s->ev_walk[3], s->stream));
+      s->walk_timed = true;
       lap("walk let");
       mark("let walk done", s->stream);
       if (evtrace) {
@@ -460,6 +479,7 @@ int finish_set(nbody_sim* s) {
   bh_reset(s->tree, s->stream);
   bh_reset(s->tree_let, s->stream);
   s->n_let = 0;
+  s->walk_timed = false;
   NB_TRY(publish_positions(s));
   NB_CUDA(cudaStreamSynchronize(s->stream));
   s->initialized = true;
@@ -581,6 +601,7 @@ void nbody_destroy(nbody_sim* s) {
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->stream_x) cudaStreamDestroy(s->stream_x);
+  for (cudaEvent_t e : s->ev_walk) if (e) cudaEventDestroy(e);
   if (s->ev_built) cudaEventDestroy(s->ev_built);
   if (s->ev_let) cudaEventDestroy(s->ev_let);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);

@@ -311,3 +311,49 @@ def test_config4_plummer_1m_theta_half(oracle):
         scale = np.abs(posm[:, 3:4].astype(np.float64) * acc[:, :3]).sum(0)
         assert np.all(np.abs(f) <= 5e-3 * scale)
     del sub
+
+
+@pytest.mark.parametrize("group_size,pack", [(32, 1), (32, 4), (64, 1), (128, 2), (64, 8)])
+def test_walk_group_shapes_keep_the_error_bar(oracle, group_size, pack):
+    """Walk-group size / packing are performance knobs: every setting stays within the reference's error and agrees with
+    the default to summation order + the (always conservative) group criterion."""
+    from parallelnbody_b200 import ic
+    posm, vel = ic.plummer(20000, seed=23)
+    exact = oracle.direct_f64(posm, eps=0.01)
+    tree = oracle.BHTree(posm, half=oracle.cube_size(posm), eps=0.01)
+    ref_err = rel_l2(tree.forces(0.3), exact)
+    tree.close()
+    with _bh(eps=0.01, theta=0.3, group_size=group_size, group_pack=pack) as s:
+        s.SetBodies(posm, vel)
+        s.CreateOctree()
+        acc = s.Accelerations()
+        st = s.Stats()
+        assert s.GroupSize == group_size and s.GroupPack == pack
+    assert rel_l2(acc, exact) <= ref_err
+    assert st["walk_groups"] * group_size >= 20000 and st["walk_groups"] <= 20000
+    assert st["interactions"] < 0.6 * 20000.0 * 20000.0
+
+
+def test_async_steps_and_device_pointers():
+    """nbody_step_async enqueues without host synchronisation; device pointers expose the resident state (zero copy)."""
+    import torch
+    from parallelnbody_b200 import ic
+    posm, vel = ic.plummer(30000, seed=29)
+    with _bh(eps=0.01, theta=0.3) as a, _bh(eps=0.01, theta=0.3) as b:
+        a.SetBodies(posm, vel); b.SetBodies(posm, vel)
+        a.Step(1e-3, 6)
+        for _ in range(3):
+            b.StepAsync(1e-3, 2)
+        b.Synchronize()
+        assert np.array_equal(a.Positions(), b.Positions()) and b.Stats()["steps"] == 6
+        p_ptr, v_ptr, a_ptr = b.DevicePtrs()
+        assert p_ptr and v_ptr and a_ptr
+        ids = b.LocalIds()
+
+        class _Raw:   # torch view of the library's float4 positions through __cuda_array_interface__
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n, 4), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        view = torch.as_tensor(_Raw(p_ptr, 30000), device="cuda")
+        got = np.zeros((30000, 4), np.float32)
+        got[ids] = view.cpu().numpy()                 # device order is the Morton order; ids maps it back
+        assert np.array_equal(got, b.Positions())
