@@ -818,10 +818,12 @@ __global__ void let_sample_kernel(const uint64_t* __restrict__ keys, const int n
 }
 
 // One CTA: sort the gathered samples by key (bitonic, shared memory) and cut them into `world` pieces of equal WEIGHT.
-// A sample of rank q stands for 1/kLetSamples of that rank's cost = a blend of its share of the bodies and its share
-// of last step's walk time (equal work, not just equal counts: dense regions cost more interactions per body).
+// A sample of rank q stands for 1/kLetSamples of that rank's cost = (1 - time_weight) x its share of the bodies +
+// time_weight x its share of last step's walk time. time_weight = 0 (default) gives equal counts; on 8 GPUs / 16M
+// two-galaxy bodies 0.7 moved the boundaries too much per step (more migration than the walks gained, 94 vs 109 steps/s).
 __global__ void __launch_bounds__(1024)
-let_splitters_kernel(const uint64_t* __restrict__ msgs, const int world, uint64_t* __restrict__ splitters) {
+let_splitters_kernel(const uint64_t* __restrict__ msgs, const int world, const float time_weight,
+                     uint64_t* __restrict__ splitters) {
   extern __shared__ uint64_t sk[];                 // [pow2] keys, then [pow2] floats (weights -> inclusive prefix)
   const int total = world * kLetSamples;
   int pow2 = 1;
@@ -841,7 +843,7 @@ let_splitters_kernel(const uint64_t* __restrict__ msgs, const int world, uint64_
       const double nq = (double)msgs[(size_t)q * kLetMsg + kLetSamples];
       const float tq = __uint_as_float((uint32_t)msgs[(size_t)q * kLetMsg + kLetSamples + 1]);
       double w = sum_n > 0 ? nq / sum_n : 1.0 / world;
-      if (timed && sum_t > 0) w = 0.3 * w + 0.7 * (double)tq / sum_t;
+      if (timed && sum_t > 0 && time_weight > 0.f) w = (1.0 - time_weight) * w + (double)time_weight * (double)tq / sum_t;
       wq[q] = (float)(w / kLetSamples);
     }
   }
@@ -1042,7 +1044,7 @@ int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, f
   NB_TRY(comm->all_gather_bytes(m->samples + (size_t)world * kLetMsg, m->samples, (size_t)kLetMsg * 8, s));
   int pow2 = 1;
   while (pow2 < world * kLetSamples) pow2 <<= 1;
-  let_splitters_kernel<<<1, 1024, (size_t)pow2 * 12, s>>>(m->samples, world, m->splitters);
+  let_splitters_kernel<<<1, 1024, (size_t)pow2 * 12, s>>>(m->samples, world, p.let_time_weight, m->splitters);
   *launches += 4;
   int sorted = 0;
   if (n > 0) {

@@ -24,6 +24,7 @@ struct BHParams {
   int mac = kMacGroup;
   int group_size = 64;  // bodies per walk group: 32, 64 or 128 (1, 2 or 4 per lane)
   bool leave_sm_slot = false;  // walk with one CTA per SM fewer than fit, so kernels of another stream can run beside it
+  float let_time_weight = 0.f; // domain split: 0 = equal body counts per rank, up to 1 = equal last-step walk time
   int depth_hint = 0;          // last known tree depth (0 = unknown): how many key levels the sort has to resolve
   int group_pack = 2;   // cells of <= group_pack * group_size bodies are cut into equal walk groups
 };

@@ -293,6 +293,7 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
     bp.group_size = s->cfg.group_size;
     bp.group_pack = s->cfg.group_pack;
     bp.depth_hint = s->tree.depth_host;
+    if (const char* tw = getenv("NBODY_LET_TIME_WEIGHT")) bp.let_time_weight = std::min(1.f, std::max(0.f, (float)atof(tw)));   // development knob
     double launches = 0;
     if (s->let_mode()) {
       // (1)-(2) splitters + body migration, (3) local tree, (4)-(5) LET exchange + tree, (6) two walks; see bh.cu K9
