@@ -295,9 +295,12 @@ def run_ours(args, wl):
     e0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(e2e_steps):
+        t_it = time.perf_counter()
         sim.SetParticlesRaw(aos_in.data_ptr(), n, 40)     # H2D: this rank's FParticle records
         sim.Tick()                                        # OctreeSearch.cpp:21-34
         sim.GetParticlesRaw(aos_out.data_ptr(), n, 40)    # D2H: this rank's FParticle records
+        if os.environ.get("NBODY_BENCH_TRACE"):
+            print(f"[bench rank {rank}] e2e iteration {1e3 * (time.perf_counter() - t_it):.2f} ms", file=sys.stderr)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - e0)
     n_local = st["n_local"]
@@ -325,6 +328,7 @@ def run_ours(args, wl):
                 "traffic": None, "kernel": "bh_walk_group_kernel", "interactions_per_step": inter_all / args.steps,
                 "ms_per_launch": ms_force / args.steps, "ms_build_per_step": ms_build / args.steps}
 
+    lets = method == "bh" and (args.bh_exchange == 0 or (args.bh_exchange < 0 and n > (1 << 25)))
     if rank != 0:
         sim.close()
         if world > 1:
@@ -340,7 +344,11 @@ def run_ours(args, wl):
                                "integrate": ms_integ / args.steps, "comm": ms_comm / args.steps},
         "wall_s_timed_region": wall,
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(n) * 40, "d2h_bytes_per_step": int(n) * 40,
+        # direct sum / domain split: every rank uploads and reads back its own share; replicated Barnes-Hut: every rank
+        # uploads all bodies and reads back its share
+        "e2e": {"value": e2e_value, "unit": unit,
+                "h2d_bytes_per_step": int(n) * 40 * (world if (method == "bh" and world > 1 and not lets) else 1),
+                "d2h_bytes_per_step": int(n) * 40,
                 "steps": e2e_steps, "api": "OctreeSearch.Particles <- pinned FParticle AoS; Tick(); Particles -> pinned AoS"},
         "gpu_launches": int(launches),
         "roofline": roof,

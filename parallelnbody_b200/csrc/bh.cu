@@ -674,11 +674,11 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
   root_cube_kernel<<<1, 1, 0, s>>>(box, p.reference_root ? 1 : 0, m->root);
   morton_kernel<<<nb, 256, 0, s>>>(posm_in, n, m->root, m->sort.keys[0]);
   *launches += 2;
-  // Sort only as many levels as the tree needs: the last known depth + 3 (a cell at the last sorted level is a leaf
+  // Sort only as many levels as the tree needs: the last known depth + 4 (a cell at the last sorted level is a leaf
   // whatever it holds, so a too-small hint costs accuracy nothing, only walk efficiency, and corrects itself through
   // the depth statistic). The parity configurations (one-body leaves / per-body walk) always sort all 63 bits.
   int levels = kMaxLevel;
-  if (p.leaf_size > 1 && p.mac == kMacGroup && p.depth_hint > 0) levels = std::min(kMaxLevel, std::max(8, p.depth_hint + 3));
+  if (p.leaf_size > 1 && p.mac == kMacGroup && p.depth_hint > 0) levels = std::min(kMaxLevel, std::max(10, p.depth_hint + 4));
   m->sorted = radix_sort_pairs(m->sort, n, 3 * kMaxLevel, s, launches, 3 * (kMaxLevel - levels));
   gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[m->sorted], n, posm_in, vel_in, ids_in, posm, vel, ids);
   const uint64_t* keys = m->sort.keys[m->sorted];
