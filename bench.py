@@ -169,7 +169,7 @@ def workload_config(args, wl, world):
             "partition": ("1 GPU" if world == 1 else
                           f"i-rows over {world} GPUs, NCCL all-gather of float4 positions per step" if method == "direct" else
                           f"Morton domain split over {world} GPUs, body migration + locally-essential-tree exchange (NCCL all-to-all-v)"
-                          if (getattr(args, "bh_exchange", -1) == 0 or (getattr(args, "bh_exchange", -1) < 0 and n > (1 << 25))) else
+                          if (getattr(args, "bh_exchange", -1) == 0 or (getattr(args, "bh_exchange", -1) < 0 and n > (1 << 23))) else
                           f"replicated tree, Morton-order slices over {world} GPUs, all-gather of positions + velocities"),
             "l2": "flushed between timed steps (256 MiB memset); sources (16 B/body) are re-read from L2 by design",
             "seed": 1234}
@@ -328,7 +328,7 @@ def run_ours(args, wl):
                 "traffic": None, "kernel": "bh_walk_group_kernel", "interactions_per_step": inter_all / args.steps,
                 "ms_per_launch": ms_force / args.steps, "ms_build_per_step": ms_build / args.steps}
 
-    lets = method == "bh" and (args.bh_exchange == 0 or (args.bh_exchange < 0 and n > (1 << 25)))
+    lets = method == "bh" and (args.bh_exchange == 0 or (args.bh_exchange < 0 and n > (1 << 23)))
     if rank != 0:
         sim.close()
         if world > 1:

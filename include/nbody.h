@@ -77,7 +77,7 @@ typedef struct nbody_config {
   int32_t bh_exchange;    /* multi-GPU Barnes-Hut: 0 = Morton domain split, body migration and locally-essential-tree exchange
                              (each rank holds only its domain); 1 = replicated tree (every rank holds all bodies, walks its
                              slice of the Morton order, all-gathers positions and velocities); -1 (default) = by size:
-                             replicated up to 2^25 bodies, domain split above */
+                             replicated up to 2^23 bodies, domain split above */
   int32_t reserved[1];
   uint8_t nccl_unique_id[128]; /* multi-GPU: the ncclUniqueId from nbody_comm_unique_id on rank 0. All zeros with world > 1 =
                                   an EMULATED rank: no communicator; the handle evaluates its slice of the bodies given by

@@ -163,8 +163,9 @@ cudaEvent_t pool_event(nbody_sim* s, size_t k) {
 // Split n bodies over the ranks: contiguous slices of n_per = ceil(n / world) (direct sum: fixed for the run).
 void partition(nbody_sim* s, int64_t n) {
   s->n_global = n;
-  // measured on 8 x B200 (profiles/): up to 16M bodies the replicated tree is faster than the domain split
-  s->exchange = s->cfg.bh_exchange >= 0 ? s->cfg.bh_exchange : (n > ((int64_t)1 << 25) ? 0 : 1);
+  // measured (profiles/): at 16M bodies the domain split wins on 4 and 8 GPUs (138 vs 117, 167 vs 159 steps/s), at 2M
+  // bodies on 2 GPUs the replicated tree wins (537 vs 432): switch at 8M
+  s->exchange = s->cfg.bh_exchange >= 0 ? s->cfg.bh_exchange : (n > ((int64_t)1 << 23) ? 0 : 1);
   s->n_per = ceil_div(n, s->cfg.world);
   s->slice_begin = std::min<int64_t>(n, (int64_t)s->cfg.rank * s->n_per);
   s->n_local = std::min<int64_t>(s->n_per, n - s->slice_begin);
