@@ -96,8 +96,10 @@ typedef struct nbody_stats {
   double kernel_launches;  /* kernels launched by this handle since creation */
   float ms_last_call;      /* device time of the last nbody_step / nbody_create_octree call (CUDA events on the
                               handle's stream), all steps of that call */
-  float ms_force;          /* same call: force kernel(s) only (direct: K1; BH: walk) */
-  float ms_build;          /* same call: BH build (bbox, keys, sort, tree, monopoles); 0 for direct */
+  float ms_force;          /* same call: force kernel(s) only (direct: K1; BH: walk; domain split: local walk beside the
+                              LET exchange + the walk of the received points) */
+  float ms_build;          /* same call: BH build (bbox, keys, sort, tree, monopoles; domain split: + body migration);
+                              0 for direct */
   float ms_integrate;      /* same call: fused reduce + kick-drift */
   float ms_comm;           /* same call: collectives */
   float cube_size;         /* AOctreeSearch::Size after the last ComputeCubeSize */
@@ -105,7 +107,7 @@ typedef struct nbody_stats {
   float root_com[3];       /* BH: root centre of mass of the last build (the next reference-mode root origin) */
   float root_mass;
   int32_t walk_groups;     /* BH: groups of the last build */
-  int32_t reserved0;
+  int32_t let_points;      /* BH domain split: locally-essential points received from the peers in the last step */
 } nbody_stats;
 
 typedef struct nbody_sim nbody_sim; /* opaque handle: owns device buffers, stream, events, NCCL communicator */

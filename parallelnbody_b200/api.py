@@ -48,7 +48,7 @@ class Stats(C.Structure):
                 ("ms_last_call", C.c_float), ("ms_force", C.c_float), ("ms_build", C.c_float),
                 ("ms_integrate", C.c_float), ("ms_comm", C.c_float), ("cube_size", C.c_float), ("jsplit", C.c_int32),
                 ("i_per_thread", C.c_int32), ("tree_nodes", C.c_int32), ("tree_depth", C.c_int32),
-                ("root_com", C.c_float * 3), ("root_mass", C.c_float), ("walk_groups", C.c_int32), ("reserved0", C.c_int32)]
+                ("root_com", C.c_float * 3), ("root_mass", C.c_float), ("walk_groups", C.c_int32), ("let_points", C.c_int32)]
 
     def as_dict(self):
         d = {}

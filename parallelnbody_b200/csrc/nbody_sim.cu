@@ -851,7 +851,7 @@ int nbody_stats_get(nbody_sim* s, nbody_stats* out) {
   out->ms_integrate = s->ms_integrate; out->ms_comm = s->ms_comm;
   out->cube_size = s->cube_size;
   out->jsplit = s->plan.jsplit; out->i_per_thread = s->plan.i_per_thread;
-  out->tree_nodes = s->tree.n_nodes_host; out->tree_depth = s->tree.depth_host; out->walk_groups = s->tree.n_groups_host;
+  out->tree_nodes = s->tree.n_nodes_host; out->tree_depth = s->tree.depth_host; out->walk_groups = s->tree.n_groups_host; out->let_points = s->n_let;
   memcpy(out->root_com, s->tree.root_com_host, sizeof(out->root_com));
   out->root_mass = s->tree.root_mass_host;
   return NBODY_OK;
