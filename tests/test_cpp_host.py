@@ -9,7 +9,13 @@ EXE = os.path.join(ROOT, "examples", "octree_search")
 
 
 def _build():
-    subprocess.check_call(["make", "-C", ROOT, "examples/octree_search"], stdout=subprocess.DEVNULL)
+    """g++ only (never `make`: the product library must not be rebuilt under a process that has it loaded)."""
+    srcs = [os.path.join(ROOT, "examples", "octree_search.cpp"), os.path.join(ROOT, "include", "nbody.hpp"),
+            os.path.join(ROOT, "include", "nbody.h")]
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(p) for p in srcs):
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), srcs[0], "-o", EXE,
+                               "-L", os.path.join(ROOT, "parallelnbody_b200"), "-lnbody_b200",
+                               "-Wl,-rpath,$ORIGIN/../parallelnbody_b200"])
     assert os.path.exists(EXE)
 
 
