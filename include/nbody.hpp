@@ -77,6 +77,7 @@ class OctreeSearch {
     Check(nbody_set_param(sim_, NBODY_PARAM_SHOW_OCTREE, ShowOctree ? 1.0 : 0.0));
     if (!Initialized || !(PhDeltaTime > 0.f)) return;
     Check(nbody_tick(sim_));
+    Size = Stats().cube_size;   // ComputeCubeSize ran at the start of the step (OctreeSearch.cpp:26)
     if (MirrorParticles) Download();
   }
   // OctreeSearch.cpp:91-97.

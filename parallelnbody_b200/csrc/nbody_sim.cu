@@ -465,7 +465,14 @@ int run_steps(nbody_sim* s, float dt, int nsteps, bool integrate, bool sync) {
     const float f = (float)nsteps / (float)timed;
     s->ms_build *= f; s->ms_force *= f; s->ms_integrate *= f; s->ms_comm *= f;
   }
-  if (s->cfg.method == NBODY_BARNES_HUT) NB_TRY(bh_fetch_stats(s->tree, s->stream, &s->interactions));
+  if (s->cfg.method == NBODY_BARNES_HUT) {
+    NB_TRY(bh_fetch_stats(s->tree, s->stream, &s->interactions));
+    // AOctreeSearch::Size as the last Tick left it: max |coordinate| at the START of that step (OctreeSearch.cpp:26,47-56)
+    uint32_t bits = 0;
+    NB_CUDA(cudaMemcpyAsync(&bits, s->d_box, 4, cudaMemcpyDeviceToHost, s->stream));
+    NB_CUDA(cudaStreamSynchronize(s->stream));
+    memcpy(&s->cube_size, &bits, 4);
+  }
   return 0;
 }
 

@@ -357,3 +357,16 @@ def test_async_steps_and_device_pointers():
         got = np.zeros((30000, 4), np.float32)
         got[ids] = view.cpu().numpy()                 # device order is the Morton order; ids maps it back
         assert np.array_equal(got, b.Positions())
+
+
+def test_tick_updates_size_like_compute_cube_size(oracle):
+    """Tick starts with ComputeCubeSize (OctreeSearch.cpp:26): afterwards Size = max |coordinate| of the pre-drift positions."""
+    from parallelnbody_b200 import ic
+    posm, vel = ic.reference_slab(4000, 1000.0, seed=6)
+    with _bh(theta=1.0, PhDeltaTime=0.01) as s:
+        s.SetBodies(posm, vel)
+        s.Tick()
+        assert s.Size == oracle.cube_size(posm)
+        before = s.Positions()
+        s.Tick()
+        assert s.Size == oracle.cube_size(before)
