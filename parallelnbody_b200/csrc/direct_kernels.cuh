@@ -121,18 +121,19 @@ __device__ __forceinline__ void interact2(const float2 X, const float2 Y, const 
   az = __ffma2_rn(w, dz, az);
 }
 
-template <int I, bool EPS0, int MINB>
-__global__ void __launch_bounds__(kDirectTPB, MINB)
+// TPB threads per CTA = sources per shared-memory tile (default 256); chunk must be a multiple of TPB.
+template <int I, bool EPS0, int MINB, int TPB = kDirectTPB>
+__global__ void __launch_bounds__(TPB, MINB)
 direct_packed_kernel(const float4* __restrict__ src, const int chunk, const float4* __restrict__ tgt,
                      const int n_tgt, const float eps2s, float4* __restrict__ partial, const int n_tgt_pad) {
   // SoA tile, double buffered: [buf][component][j]
-  __shared__ __align__(16) float tile[2][4][kDirectTJ];
+  __shared__ __align__(16) float tile[2][4][TPB];
   const int t = threadIdx.x;
-  const int i_base = blockIdx.x * (kDirectTPB * I);
+  const int i_base = blockIdx.x * (TPB * I);
   float2 nxi[I], nyi[I], nzi[I], ax[I], ay[I], az[I];
 #pragma unroll
   for (int k = 0; k < I; k++) {
-    int i = i_base + k * kDirectTPB + t;
+    int i = i_base + k * TPB + t;
     i = i < n_tgt ? i : n_tgt - 1;
     const float4 p = tgt[i];
     nxi[k] = f2(-p.x, -p.x); nyi[k] = f2(-p.y, -p.y); nzi[k] = f2(-p.z, -p.z);
@@ -140,15 +141,15 @@ direct_packed_kernel(const float4* __restrict__ src, const int chunk, const floa
   }
   const float2 eps2 = f2(eps2s, eps2s);
   const float4* s = src + (size_t)blockIdx.y * chunk;
-  const int ntiles = chunk / kDirectTJ;
+  const int ntiles = chunk / TPB;
   float4 nxt = s[t];
   for (int tl = 0; tl < ntiles; tl++) {
     const int b = tl & 1;
     tile[b][0][t] = nxt.x; tile[b][1][t] = nxt.y; tile[b][2][t] = nxt.z; tile[b][3][t] = nxt.w;
     __syncthreads();
-    if (tl + 1 < ntiles) nxt = s[(size_t)(tl + 1) * kDirectTJ + t];
+    if (tl + 1 < ntiles) nxt = s[(size_t)(tl + 1) * TPB + t];
 #pragma unroll 4
-    for (int j = 0; j < kDirectTJ; j += 4) {
+    for (int j = 0; j < TPB; j += 4) {
       const float4 X = *reinterpret_cast<const float4*>(&tile[b][0][j]);
       const float4 Y = *reinterpret_cast<const float4*>(&tile[b][1][j]);
       const float4 Z = *reinterpret_cast<const float4*>(&tile[b][2][j]);
@@ -165,7 +166,7 @@ direct_packed_kernel(const float4* __restrict__ src, const int chunk, const floa
   float4* out = partial + (size_t)blockIdx.y * n_tgt_pad;
 #pragma unroll
   for (int k = 0; k < I; k++) {
-    const int i = i_base + k * kDirectTPB + t;
+    const int i = i_base + k * TPB + t;
     if (i < n_tgt) out[i] = make_float4(ax[k].x + ax[k].y, ay[k].x + ay[k].y, az[k].x + az[k].y, 0.f);
   }
 }

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <string>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../parallelnbody_b200/csrc/direct_kernels.cuh"
@@ -141,7 +142,49 @@ template <int I, bool E0, int MINB> void launch_packed(dim3 g, const float4* s, 
   direct_packed_kernel<I, E0, MINB><<<g, kDirectTPB>>>(s, chunk, t, nt, e2, p, npad);
 }
 
+// ---- (I, TPB) sweep of the packed kernel: more warps per SM vs more targets per thread
+template <int I, int TPB, int MINB> static float time_packed(const float4* src, int n, int jsplit, float4* partial) {
+  const int itile = TPB * I, nit = (n + itile - 1) / itile, chunk = n / jsplit;
+  dim3 g(nit, jsplit);
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  direct_packed_kernel<I, false, MINB, TPB><<<g, TPB>>>(src, chunk, src, n, 1e-4f, partial, n);
+  CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < 3; r++) {
+    CK(cudaEventRecord(e0));
+    direct_packed_kernel<I, false, MINB, TPB><<<g, TPB>>>(src, chunk, src, n, 1e-4f, partial, n);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = fminf(best, ms);
+  }
+  double ips = (double)n * n / (best * 1e-3);
+  printf("SWEEP packed I=%d TPB=%d minb=%d jsplit=%d grid=%dx%d  ms=%8.3f  inter/s=%.4e  TFLOP/s(20)=%6.2f\n", I, TPB, MINB, jsplit, nit, jsplit,
+         best, ips, ips * 20e-12);
+  return best;
+}
+
+static int sweep_main() {
+  const int n = 7680 * 48;   // divisible by 8 * {256, 320, 384, 512}
+  std::vector<float4> h(n);
+  srand(1234);
+  for (int i = 0; i < n; i++) { h[i].x = 2.f * rand() / RAND_MAX - 1.f; h[i].y = 2.f * rand() / RAND_MAX - 1.f; h[i].z = 2.f * rand() / RAND_MAX - 1.f; h[i].w = 1e-4f / n; }
+  float4 *d_src, *d_partial;
+  CK(cudaMalloc(&d_src, (size_t)n * sizeof(float4)));
+  CK(cudaMalloc(&d_partial, (size_t)8 * n * sizeof(float4)));
+  CK(cudaMemcpy(d_src, h.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+  time_packed<8, 256, 1>(d_src, n, 8, d_partial);
+  time_packed<6, 320, 1>(d_src, n, 8, d_partial);
+  time_packed<5, 384, 1>(d_src, n, 8, d_partial);
+  time_packed<6, 384, 1>(d_src, n, 8, d_partial);
+  time_packed<4, 512, 1>(d_src, n, 8, d_partial);
+  time_packed<4, 384, 1>(d_src, n, 8, d_partial);
+  time_packed<4, 256, 2>(d_src, n, 8, d_partial);
+  time_packed<3, 320, 2>(d_src, n, 8, d_partial);
+  time_packed<8, 256, 1>(d_src, n, 8, d_partial);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "sweep") return sweep_main();
   int n = argc > 1 ? atoi(argv[1]) : 262144;
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   int sms = prop.multiProcessorCount;
