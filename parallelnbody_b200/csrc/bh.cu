@@ -697,7 +697,7 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
       NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split_ctas, tree_split_kernel, 256, 0));
       split_ctas = std::max(1, std::min(split_ctas, 8));
     }
-    NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(kNumSMsB200 * (p.leave_sm_slot ? 1 : split_ctas)), dim3(256), args, 0, s));
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(sm_count() * (p.leave_sm_slot ? 1 : split_ctas)), dim3(256), args, 0, s));
   }
   monopole_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
   *launches += 2;
@@ -1106,7 +1106,7 @@ int bh_let_exchange(BHState& local, BHState& let, Comm* comm, const BHParams& p,
     float theta2 = p.theta * p.theta;
     void* args[] = {(void*)&posm, &m->node_com, &m->node_meta, &m->counters, &m->root, &m->peer_boxes, &w, &r, &theta2, &m->visit,
                     &m->let_out, &m->let_cnt, &cap_let};
-    NB_CUDA(cudaLaunchCooperativeKernel((void*)let_export_kernel, dim3(kNumSMsB200), dim3(256), args, 0, s));
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)let_export_kernel, dim3(sm_count()), dim3(256), args, 0, s));
     *launches += 1;
   }
   NB_TRY(comm->all_gather_bytes(m->let_cnt, m->all_off, (size_t)world * 4, s));

@@ -33,6 +33,15 @@ struct Status {
 
 constexpr int kNumSMsB200 = 148;
 
+// SMs of the current device (148 on a full B200). Cooperative launches must not exceed what is co-resident, so their
+// grids are sized from this, not from the constant.
+inline int sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    return kNumSMsB200;
+  return sms;
+}
+
 __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
