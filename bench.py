@@ -111,61 +111,131 @@ def dist_env():
     return f()
 
 
-# ------------------------------------------------------------------------------------------ reference arm
+# ------------------------------------------------------------------------------------------ reference (CPU) legs
+TARGETS_PER_THREAD = 16     # targets per step and host thread of the bounded Theta = 0 sample (dynamic,1 schedule: all busy)
+
+
+class RefDirectSampler:
+    """The reference's own all-pairs evaluation = its tree walk at Theta = 0 (Octree::ComputeForces, OctreeSearch.h:99-108;
+    the compiled, unmodified reference in oracle/_ref/liboracle_ref.so), timed on a bounded sample of targets against ALL
+    sources with every host thread this process may use. One step = TARGETS_PER_THREAD x threads targets. Falls back to the
+    restated fp32 loop (oracle/nbody_oracle.c) where the reference build is absent. Shared by `--impl reference` and the
+    in-line cpu_baseline so that the two report the same quantity."""
+
+    def __init__(self, posm, vel, eps):
+        from oracle import oracle as O
+        self.O, self.posm, self.eps, self.n = O, posm, eps, posm.shape[0]
+        self.kind = "reference" if O.have_ref() else "port"
+        self.threads = O.host_threads()
+        self.per_step = int(min(self.n, TARGETS_PER_THREAD * self.threads))
+        self.k = 0
+        self.t_setup = 0.0
+        if self.kind == "reference":
+            t0 = time.perf_counter()
+            self.r = O.RefSim()
+            self.r.SetParticles(O.to_aos(posm, vel))
+            self.r.ComputeCubeSize()
+            self.r.CreateOctree()            # tree build + monopoles + the shipped Theta = 1.0 walk: set-up, not timed
+            self.t_setup = time.perf_counter() - t0
+
+    def step(self) -> float:
+        i0 = (self.k * self.per_step) % max(self.n - self.per_step, 1)
+        self.k += 1
+        if self.kind == "reference":
+            return self.r.ComputeForces(0.0, i0, i0 + self.per_step, self.threads)
+        _, t = self.O.direct_f32(self.posm, eps=self.eps, i0=i0, i1=i0 + self.per_step, nthreads=self.threads, return_time=True)
+        return t
+
+    def describe(self) -> str:
+        what = ("reference tree walk at Theta=0 (OctreeSearch.h:99-108, eps=0 as shipped)" if self.kind == "reference"
+                else "restated fp32 direct loop (oracle/nbody_oracle.c)")
+        return (f"{what}: {self.per_step} targets x all {self.n} sources per step, {self.threads} busy OpenMP threads "
+                f"(schedule dynamic,1 over targets); tree build ({self.t_setup:.1f} s, single thread) and integrator excluded")
+
+    def close(self):
+        if self.kind == "reference":
+            self.r.close()
+
+
+def ref_full_tick(n: int = 1 << 16, ticks: int = 3):
+    """Second stated figure: the reference's complete Tick as shipped (OctreeSearch.cpp:21-34: cube size, octree build,
+    monopoles, Theta = 1.0 walk, kick-drift) - single thread, which is how the actor runs inside UE."""
+    from oracle import oracle as O
+    if not O.have_ref():
+        return None
+    posm, vel = make_ic("plummer", n)
+    r = O.RefSim()
+    r.SetParticles(O.to_aos(posm, vel))
+    r.PhDeltaTime = 1e-3
+    r.Tick(1)
+    t = r.Tick(ticks) / ticks
+    r.close()
+    return {"value": 1.0 / t, "unit": "steps/s", "ms_per_step": 1e3 * t, "cores": 1, "N": n,
+            "what": "reference AOctreeSearch::Tick exactly as shipped (build + monopoles + Theta=1.0 walk + kick-drift), Plummer"}
+
+
+def ref_bh_steps(wl, threads: int):
+    """Barnes-Hut config on the reference's CPU code: one single-threaded build (as shipped) + its walk at the config's
+    Theta on a sample of targets with all host threads, extrapolated to all N targets."""
+    from oracle import oracle as O
+    icname, n, method, eps, theta, dt = wl
+    if not O.have_ref():
+        return None
+    posm, vel = make_ic(icname, n)
+    r = O.RefSim()
+    r.SetParticles(O.to_aos(posm, vel))
+    r.PhDeltaTime = dt
+    r.ComputeCubeSize()
+    t0 = time.perf_counter()
+    r.CreateOctree()
+    t_build = time.perf_counter() - t0
+    m = int(min(n, 2048 * threads))
+    t = r.ComputeForces(theta, 0, m, threads)
+    r.close()
+    return {"value": 1.0 / (t_build + t * n / m), "unit": "steps/s", "cores": threads, "kind": "reference",
+            "sample": f"reference CreateOctree (single thread, incl. its shipped Theta=1 walk: {t_build:.2f} s) + ComputeForces at "
+                      f"Theta={theta} for {m} of {n} targets on {threads} threads ({t:.2f} s), extrapolated to all targets"}
+
+
 def run_reference(args, wl):
-    """The reference's own CPU implementation of the path, on the host cores. Direct sum = its tree walk at Theta = 0
-    (Octree::ComputeForces, OctreeSearch.h:99-108 - the only all-pairs evaluation the reference has); the compiled,
-    unmodified reference lives in oracle/_ref/liboracle_ref.so (oracle/Makefile)."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores, same metric and config."""
     rank, _, world = dist_env()
     if rank != 0:
         return
-    from oracle import oracle as O
     icname, n, method, eps, theta, dt = wl
     posm, vel = make_ic(icname, n)
-    kind = "reference" if O.have_ref() else "port"
-    threads = O.ref_max_threads() if kind == "reference" else O.max_threads()
-    per_step = 4 * threads          # targets per step: ~1 s of host work per step at N = 1M
+    smp = RefDirectSampler(posm, vel, eps)
     times = []
-    if kind == "reference":
-        r = O.RefSim()
-        r.SetParticles(O.to_aos(posm, vel))
-        r.ComputeCubeSize()
-        r.CreateOctree()             # tree build + the shipped Theta = 1.0 walk: set-up, not timed
-        th = 0.0 if method == "direct" else theta
-        for k in range(args.warmup + args.steps):
-            i0 = (k * per_step) % max(n - per_step, 1)
-            t = r.ComputeForces(th, i0, min(n, i0 + per_step), threads)
-            if k >= args.warmup:
-                times.append(t)
-        sample = (f"reference tree walk at Theta={th:g} (OctreeSearch.h:99-108, eps=0 as shipped) for {per_step} targets "
-                  f"x all {n} sources per step, {threads} OpenMP threads over targets; tree build excluded")
-        r.close()
-    else:
-        for k in range(args.warmup + args.steps):
-            i0 = (k * per_step) % max(n - per_step, 1)
-            _, t = O.direct_f32(posm, eps=eps, i0=i0, i1=min(n, i0 + per_step), nthreads=threads, return_time=True)
-            if k >= args.warmup:
-                times.append(t)
-        sample = f"restated fp32 direct loop for {per_step} targets x {n} sources per step, {threads} threads"
+    for k in range(args.warmup + args.steps):
+        t = smp.step()
+        if k >= args.warmup:
+            times.append(t)
     total = float(sum(times))
-    value = per_step * float(n) * len(times) / total
+    value = smp.per_step * float(n) * len(times) / total
     line = {
         "impl": "reference", "metric": "all-pairs interactions/s", "value": value, "unit": "interactions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, wl, 1),
-        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": threads, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": smp.threads, "busy_threads": smp.threads,
+                         "kind": smp.kind, "sample": smp.describe()},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    smp.close()
+    if not args.no_extras:
+        line["full_tick"] = ref_full_tick()
+        if n >= (1 << 20):
+            line["bh"] = ref_bh_steps(WORKLOADS["plummer_1m_bh"], smp.threads)
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, wl, world):
+def workload_config(args, wl, world, name=None):
     icname, n, method, eps, theta, dt = wl
     return {"workload": f"{icname} N={n} {'softened direct sum' if method == 'direct' else 'Barnes-Hut'} + kick-drift",
-            "name": args.workload, "N": n, "eps": eps, "dt": dt, "G": 1e4, "method": method,
+            "name": name or args.workload, "N": n, "eps": eps, "dt": dt, "G": 1e4, "method": method,
             "theta_reference_convention": theta if method == "bh" else 0.0,
+            "theta_conventional": 2 * theta if method == "bh" else 0.0,
             "partition": ("1 GPU" if world == 1 else
                           f"i-rows over {world} GPUs, NCCL all-gather of float4 positions per step" if method == "direct" else
                           f"Morton domain split over {world} GPUs, body migration + locally-essential-tree exchange (NCCL all-to-all-v)"
@@ -175,65 +245,203 @@ def workload_config(args, wl, world):
             "seed": 1234}
 
 
-def cpu_baseline(wl, budget_s: float = 20.0):
+def cpu_baseline(wl, posm, vel, budget_s: float = 15.0):
     """Bounded sample of the reference's CPU code on this host (rank 0, N=1 only)."""
-    from oracle import oracle as O
     icname, n, method, eps, theta, dt = wl
-    posm, vel = make_ic(icname, n)
-    if O.have_ref() and method == "direct":
-        threads = O.ref_max_threads()
-        r = O.RefSim()
-        r.SetParticles(O.to_aos(posm, vel))
-        r.ComputeCubeSize()
-        r.CreateOctree()
-        m = 2 * threads
-        t = r.ComputeForces(0.0, 0, m, threads)
-        # scale the sample to ~budget/2 seconds
-        m2 = int(min(n, max(m, m * (0.5 * budget_s) / max(t, 1e-3))))
-        t2 = r.ComputeForces(0.0, 0, m2, threads)
-        r.close()
-        _, tp = O.direct_f32(posm, eps=eps, i0=0, i1=min(n, 16 * threads), nthreads=threads, return_time=True)
-        return {"value": m2 * float(n) / t2, "unit": "interactions/s", "cores": threads, "kind": "reference",
-                "sample": f"reference Theta=0 tree walk (OctreeSearch.h:99-108), {m2} targets x {n} sources, {threads} threads, tree build excluded",
-                "port_value": min(n, 16 * threads) * float(n) / tp,
-                "port_sample": f"restated fp32 double loop (oracle/nbody_oracle.c), {min(n, 16 * threads)} targets x {n} sources, {threads} threads"}
-    if O.have_ref():
-        threads = 1
-        r = O.RefSim()
-        r.SetParticles(O.to_aos(posm, vel))
-        r.PhDeltaTime = dt
-        r.ComputeCubeSize()
-        t0 = time.perf_counter()
-        r.CreateOctree()
-        t_build = time.perf_counter() - t0
-        m = int(min(n, 20000))
-        t = r.ComputeForces(theta, 0, m, O.ref_max_threads())
-        r.close()
-        return {"value": 1.0 / (t_build + t * n / m / 1.0), "unit": "steps/s", "cores": O.ref_max_threads(), "kind": "reference",
-                "sample": f"reference build (single thread, incl. shipped Theta=1 walk) + Theta={theta} walk extrapolated from {m} targets"}
-    threads = O.max_threads()
-    m = 16 * threads
-    _, tp = O.direct_f32(posm, eps=eps, i0=0, i1=min(n, m), nthreads=threads, return_time=True)
-    return {"value": min(n, m) * float(n) / tp, "unit": "interactions/s", "cores": threads, "kind": "port",
-            "sample": f"restated fp32 double loop, {min(n, m)} targets x {n} sources"}
+    from oracle import oracle as O
+    if method != "direct":
+        return ref_bh_steps(wl, O.host_threads())
+    smp = RefDirectSampler(posm, vel, eps)
+    smp.step()
+    times, t_all = [], 0.0
+    while t_all < budget_s and len(times) < 64:
+        times.append(smp.step())
+        t_all += times[-1]
+    out = {"value": smp.per_step * float(n) * len(times) / t_all, "unit": "interactions/s", "cores": smp.threads,
+           "busy_threads": smp.threads, "kind": smp.kind, "sample": smp.describe() + f"; {len(times)} steps"}
+    smp.close()
+    m = int(min(n, 16 * smp.threads))
+    _, tp = O.direct_f32(posm, eps=eps, i0=0, i1=m, nthreads=smp.threads, return_time=True)
+    out["port_value"] = m * float(n) / tp
+    out["port_sample"] = f"restated fp32 double loop (oracle/nbody_oracle.c), {m} targets x {n} sources, {smp.threads} threads"
+    return out
+
+
+def load_traffic(kernel: str, workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture of this
+    workload (profiles/traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(workload, {}).get(kernel)
+    except (OSError, ValueError):
+        return None
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def run_ours(args, wl):
+def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_baseline=False):
+    """One workload on the product path: device-resident timing, end-to-end timing, roofline. Returns the dict of results
+    (rank 0) or None."""
+    import torch
+    import parallelnbody_b200 as P
+    from parallelnbody_b200.api import to_particles
+    wl = WORKLOADS[name]
+    icname, n, method, eps, theta, dt = wl
+    rank, local_rank, world, uid_fn, barrier, max_over_ranks, sum_over_ranks, flush_l2, peak_tf, peak_mhz = ctx
+    posm, vel = make_ic(icname, n)
+    meth = P.METHOD_DIRECT if method == "direct" else P.METHOD_BARNES_HUT
+    sim = P.OctreeSearch(method=meth, G=1e4, eps=eps, theta=theta if method == "bh" else 0.0, PhDeltaTime=dt,
+                         device=local_rank, rank=rank, world=world, nccl_unique_id=uid_fn(), bh_exchange=args.bh_exchange)
+    sim.SetBodies(posm, vel)
+    lets = method == "bh" and world > 1 and (args.bh_exchange == 0 or (args.bh_exchange < 0 and n > (1 << 23)))
+
+    # ---- device-resident: value
+    for _ in range(warmup):
+        sim.Step(dt, 1)
+    if min_seconds > 0:   # size the timed region from the warmed-up step time (the same count on every rank)
+        est = max_over_ranks(sim.Stats()["ms_last_call"] * 1e-3)
+        steps = int(max(steps, min(20000, np.ceil(min_seconds / max(est, 1e-5)))))
+    l0 = sim.Stats()["kernel_launches"]
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    wall0 = time.perf_counter()
+    ms = {"total": 0.0, "force": 0.0, "build": 0.0, "integrate": 0.0, "comm": 0.0}
+    interactions = 0.0
+    for _ in range(steps):
+        flush_l2()
+        sim.Step(dt, 1)
+        st = sim.Stats()
+        ms["total"] += st["ms_last_call"]; ms["force"] += st["ms_force"]; ms["build"] += st["ms_build"]
+        ms["integrate"] += st["ms_integrate"]; ms["comm"] += st["ms_comm"]
+        interactions += st["interactions"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    clk = clocks.stop() if rank == 0 else None
+    launches = sim.Stats()["kernel_launches"] - l0
+    ms_total_max = max_over_ranks(ms["total"])
+    inter_all = sum_over_ranks(interactions)
+    local_pairs = st["n_local"] * float(n)
+    phase_max = {k: max_over_ranks(v) / steps for k, v in ms.items() if k != "total"}
+    n_local_max, n_local_min = max_over_ranks(float(st["n_local"])), -max_over_ranks(-float(st["n_local"]))
+    let_max = max_over_ranks(float(st["let_points"]))
+
+    # ---- end to end through the public API with HOST buffers (pinned FParticle arrays in, Tick, FParticle arrays out)
+    aos_in = torch.empty(n * 40, dtype=torch.uint8).pin_memory()
+    aos_out = torch.empty(n * 40, dtype=torch.uint8).pin_memory()
+    aos_in.numpy().view(P.PARTICLE_DTYPE)[:] = to_particles(posm, vel)
+    sim.SetParticlesRaw(aos_in.data_ptr(), n, 40); sim.Tick(); sim.GetParticlesRaw(aos_out.data_ptr(), n, 40)  # warm
+    e2e_steps = max(1, min(steps, args.e2e_steps if method == "direct" else max(args.e2e_steps, 20)))
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        t_it = time.perf_counter()
+        sim.SetParticlesRaw(aos_in.data_ptr(), n, 40)     # H2D: this rank's FParticle records
+        sim.Tick()                                        # OctreeSearch.cpp:21-34
+        sim.GetParticlesRaw(aos_out.data_ptr(), n, 40)    # D2H: this rank's FParticle records
+        if os.environ.get("NBODY_BENCH_TRACE"):
+            print(f"[bench rank {rank}] e2e iteration {1e3 * (time.perf_counter() - t_it):.2f} ms", file=sys.stderr)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - e0)
+    stats = sim.Stats()
+    sim.close()
+
+    if method == "direct":
+        metric, unit = "all-pairs interactions/s", "interactions/s"
+        value = float(n) * float(n) * steps / (ms_total_max * 1e-3)
+        e2e_value = float(n) * float(n) * e2e_steps / e2e_s
+        ach = FLOPS_PER_INTERACTION * local_pairs * steps / (ms["force"] * 1e-3) / 1e12
+        roof = {"bound": "fp32", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": load_traffic("direct_packed_kernel", name) if world == 1 else None,
+                "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                "algorithmic_bytes": 16.0 * n + 16.0 * st["n_local"] * stats["jsplit"],
+                "peak_kind": f"measured FFMA-chain burst on this GPU ({peak_mhz:.0f} MHz); MEASURED_PEAKS.json has no FP32 entry",
+                "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_nominal": ach / FP32_NOMINAL_TFLOPS,
+                "kernel": "direct_packed_kernel", "flops_per_interaction": FLOPS_PER_INTERACTION,
+                "ms_per_launch": ms["force"] / steps, "jsplit": stats["jsplit"], "i_per_thread": stats["i_per_thread"],
+                "equal_mass_kernel": bool(stats.get("equal_mass", 0))}
+    else:
+        metric, unit = "Barnes-Hut steps/s", "steps/s"
+        value = steps / (ms_total_max * 1e-3)
+        e2e_value = e2e_steps / e2e_s
+        ach = FLOPS_PER_INTERACTION * interactions / (ms["force"] * 1e-3) / 1e12
+        hbm = measured_hbm_gbs()
+        nl = float(st["n_local"]) if lets else float(n)
+        build_bytes = bh_build_bytes(nl, stats)
+        build_gbs = build_bytes / max(ms["build"] / steps * 1e-3, 1e-9) / 1e9
+        roof = {"bound": "fp32", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": load_traffic("bh_walk_group_kernel", name) if world == 1 else None,
+                "kernel": "bh_walk_group_kernel", "interactions_per_step": inter_all / steps,
+                "interactions_per_body": inter_all / steps / n, "flops_per_interaction": FLOPS_PER_INTERACTION,
+                "ms_per_launch": ms["force"] / steps,
+                "build": {"bound": "hbm", "achieved": build_gbs, "peak": hbm, "unit": "GB/s", "frac": build_gbs / hbm,
+                          "algorithmic_bytes": build_bytes, "ms": ms["build"] / steps,
+                          "peak_kind": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback 6550.7 GB/s (B200_PROFILING.md)",
+                          "what": "cube size + Morton keys + radix sort passes + body gather + tree split + monopoles, algorithmic bytes (DESIGN.md section 4)"}}
+    if rank != 0:
+        return None
+    res = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_total_max / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl, world, name),
+        "tflops_20flop": FLOPS_PER_INTERACTION * value / 1e12 if method == "direct" else None,
+        "frac_fp32_peak_per_gpu": (FLOPS_PER_INTERACTION * value / 1e12 / world / peak_tf) if method == "direct" else None,
+        "phases_ms_per_step": {k: ms[k] / steps for k in ("force", "build", "integrate", "comm")},
+        "phases_ms_per_step_max_over_ranks": phase_max,
+        "longest_phase": max(phase_max, key=phase_max.get),
+        "wall_s_timed_region": wall,
+        "clocks": clk,
+        # direct sum / domain split: every rank uploads and reads back its own share; replicated Barnes-Hut: every rank
+        # uploads all bodies and reads back its share
+        "e2e": {"value": e2e_value, "unit": unit,
+                "h2d_bytes_per_step": int(n) * 40 * (world if (method == "bh" and world > 1 and not lets) else 1),
+                "d2h_bytes_per_step": int(n) * 40,
+                "steps": e2e_steps, "api": "OctreeSearch.Particles <- pinned FParticle AoS; Tick(); Particles -> pinned AoS"},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+    }
+    if method == "bh":
+        res["bodies_per_rank"] = {"min": n_local_min, "max": n_local_max}
+        res["let_points_max"] = let_max
+        res["tree"] = {"nodes": stats["tree_nodes"], "depth": stats["tree_depth"], "walk_groups": stats["walk_groups"]}
+    if with_cpu_baseline:
+        res["cpu_baseline"] = cpu_baseline(wl, posm, vel)
+    return res
+
+
+def measured_hbm_gbs() -> float:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except (OSError, ValueError, KeyError):
+        return 6550.7
+
+
+def bh_build_bytes(n: float, stats: dict) -> float:
+    """Algorithmic bytes of one Barnes-Hut build over n bodies: cube size 16n; keys 16n r + 8n w; each
+    radix pass 12n r + 12n w (+ one 8n histogram read of the keys); body gather 4n + 36n r + 36n w; tree split: keys 8n r +
+    40 B per node; monopoles 16n r + 48 B per node."""
+    passes = float(stats.get("sort_passes", 0)) or 8.0
+    nodes = float(stats["tree_nodes"])
+    return n * (16 + 24 + 8 + passes * 24 + 76 + 8 + 16) + nodes * (40 + 48)
+
+
+def run_ours(args):
     import torch
     import torch.distributed as dist
     import parallelnbody_b200 as P
 
     rank, local_rank, world = dist_env()
-    icname, n, method, eps, theta, dt = wl
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     from parallelnbody_b200 import launch
-    uid = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        uid = launch.broadcast_unique_id(P.comm_unique_id, dist, device="cuda")
+
+    def uid_fn():     # one fresh NCCL id per handle
+        return launch.broadcast_unique_id(P.comm_unique_id, dist, device="cuda") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -246,117 +454,27 @@ def run_ours(args, wl):
     def sum_over_ranks(x: float) -> float:
         return launch.reduce_scalar(x, dist, "sum", device="cuda") if world > 1 else x
 
-    posm, vel = make_ic(icname, n)
-    meth = P.METHOD_DIRECT if method == "direct" else P.METHOD_BARNES_HUT
-    sim = P.OctreeSearch(method=meth, G=1e4, eps=eps, theta=theta if method == "bh" else 0.0, PhDeltaTime=dt,
-                         device=local_rank, rank=rank, world=world, nccl_unique_id=uid, bh_exchange=args.bh_exchange)
-    sim.SetBodies(posm, vel)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def flush_l2():
         flush.zero_()
         torch.cuda.synchronize()
 
-    # ---- device-resident: value
-    for _ in range(args.warmup):
-        sim.Step(dt, 1)
     peak_tf, peak_mhz = P.measure_fp32_peak(local_rank)   # FFMA-chain burst peak, same process, same GPU
-    l0 = sim.Stats()["kernel_launches"]
-    clocks = ClockSampler(local_rank)
+    ctx = (rank, local_rank, world, uid_fn, barrier, max_over_ranks, sum_over_ranks, flush_l2, peak_tf, peak_mhz)
+    main_wl = WORKLOADS[args.workload]
+    line = run_workload(args, args.workload, ctx, args.steps, args.warmup,
+                        min_seconds=2.0 if main_wl[2] == "bh" else 0.0,
+                        with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+    # BASELINE.json's metric has a second half - "BH steps/s": the default run measures it too and attaches it as `bh`
+    if args.workload == "plummer_1m_direct" and not args.no_bh:
+        bh_name = "plummer_1m_bh" if world == 1 else "two_galaxies_16m_bh"
+        bh = run_workload(args, bh_name, ctx, args.steps, max(args.warmup, 3), min_seconds=2.0,
+                          with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+        if rank == 0:
+            line["bh"] = bh
     if rank == 0:
-        clocks.start()
-    barrier()
-    wall0 = time.perf_counter()
-    ms_total = ms_force = ms_build = ms_integ = ms_comm = 0.0
-    interactions = 0.0
-    for _ in range(args.steps):
-        flush_l2()
-        sim.Step(dt, 1)
-        st = sim.Stats()
-        ms_total += st["ms_last_call"]; ms_force += st["ms_force"]; ms_build += st["ms_build"]
-        ms_integ += st["ms_integrate"]; ms_comm += st["ms_comm"]
-        interactions += st["interactions"]
-    barrier()
-    wall = time.perf_counter() - wall0
-    clk = clocks.stop() if rank == 0 else None
-    launches = sim.Stats()["kernel_launches"] - l0
-    ms_total_max = max_over_ranks(ms_total)
-    inter_all = sum_over_ranks(interactions)
-    pairs_all = float(n) * float(n) * args.steps
-    local_pairs = st["n_local"] * float(n)
-
-    # ---- end to end through the public API with host buffers
-    aos_in = torch.empty(n * 40, dtype=torch.uint8).pin_memory()
-    aos_out = torch.empty(n * 40, dtype=torch.uint8).pin_memory()
-    from parallelnbody_b200.api import to_particles
-    aos_in.numpy().view(P.PARTICLE_DTYPE)[:] = to_particles(posm, vel)
-    sim.SetParticlesRaw(aos_in.data_ptr(), n, 40); sim.Tick(); sim.GetParticlesRaw(aos_out.data_ptr(), n, 40)  # warm
-    barrier()
-    e0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(e2e_steps):
-        t_it = time.perf_counter()
-        sim.SetParticlesRaw(aos_in.data_ptr(), n, 40)     # H2D: this rank's FParticle records
-        sim.Tick()                                        # OctreeSearch.cpp:21-34
-        sim.GetParticlesRaw(aos_out.data_ptr(), n, 40)    # D2H: this rank's FParticle records
-        if os.environ.get("NBODY_BENCH_TRACE"):
-            print(f"[bench rank {rank}] e2e iteration {1e3 * (time.perf_counter() - t_it):.2f} ms", file=sys.stderr)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - e0)
-    n_local = st["n_local"]
-
-    if method == "direct":
-        metric, unit = "all-pairs interactions/s", "interactions/s"
-        value = pairs_all / (ms_total_max * 1e-3)
-        e2e_value = float(n) * float(n) * e2e_steps / e2e_s
-        ach = FLOPS_PER_INTERACTION * local_pairs * args.steps / (ms_force * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed ncu --set full capture of this
-        # workload (profiles/r1_direct_kernel_ncu_summary.md): 40.2 MB read + 223.4 MB written, against 16.8 MB of sources
-        # + 268 MB of j-split partials; irrelevant to the bound (0.6 GB/s-class traffic in a 413 ms kernel)
-        traffic = 263.66e6 if (args.workload == "plummer_1m_direct" and world == 1) else None
-        roof = {"bound": "fp32", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": traffic, "peak_kind": f"measured FFMA-chain burst on this GPU ({peak_mhz:.0f} MHz); MEASURED_PEAKS.json has no FP32 entry",
-                "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_nominal": ach / FP32_NOMINAL_TFLOPS,
-                "kernel": "direct_packed_kernel", "flops_per_interaction": FLOPS_PER_INTERACTION,
-                "ms_per_launch": ms_force / args.steps}
-    else:
-        metric, unit = "Barnes-Hut steps/s", "steps/s"
-        value = args.steps / (ms_total_max * 1e-3)
-        e2e_value = e2e_steps / e2e_s
-        ach = FLOPS_PER_INTERACTION * interactions / (ms_force * 1e-3) / 1e12
-        roof = {"bound": "fp32", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "kernel": "bh_walk_group_kernel", "interactions_per_step": inter_all / args.steps,
-                "ms_per_launch": ms_force / args.steps, "ms_build_per_step": ms_build / args.steps}
-
-    lets = method == "bh" and (args.bh_exchange == 0 or (args.bh_exchange < 0 and n > (1 << 23)))
-    if rank != 0:
-        sim.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    line = {
-        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl, world),
-        "tflops_20flop": FLOPS_PER_INTERACTION * value / 1e12 if method == "direct" else None,
-        "frac_fp32_peak_per_gpu": (FLOPS_PER_INTERACTION * value / 1e12 / world / peak_tf) if method == "direct" else None,
-        "phases_ms_per_step": {"force": ms_force / args.steps, "build": ms_build / args.steps,
-                               "integrate": ms_integ / args.steps, "comm": ms_comm / args.steps},
-        "wall_s_timed_region": wall,
-        "clocks": clk,
-        # direct sum / domain split: every rank uploads and reads back its own share; replicated Barnes-Hut: every rank
-        # uploads all bodies and reads back its share
-        "e2e": {"value": e2e_value, "unit": unit,
-                "h2d_bytes_per_step": int(n) * 40 * (world if (method == "bh" and world > 1 and not lets) else 1),
-                "d2h_bytes_per_step": int(n) * 40,
-                "steps": e2e_steps, "api": "OctreeSearch.Particles <- pinned FParticle AoS; Tick(); Particles -> pinned AoS"},
-        "gpu_launches": int(launches),
-        "roofline": roof,
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl)
-    print(json.dumps(line), flush=True)
-    sim.close()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -372,6 +490,8 @@ def main():
     ap.add_argument("--bh-exchange", type=int, default=-1, choices=[-1, 0, 1],
                     help="multi-GPU Barnes-Hut: 0 = Morton domain split + LET exchange, 1 = replicated tree")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bh", action="store_true", help="skip the Barnes-Hut object of the default run")
+    ap.add_argument("--no-extras", action="store_true", help="reference arm: skip the full-Tick and Barnes-Hut figures")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("bench.py: note: fewer than 3 warm-up steps", file=sys.stderr)
@@ -387,7 +507,7 @@ def main():
                    "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
             raise SystemExit(subprocess.call(cmd))
         raise SystemExit(f"WORLD_SIZE={world} but --gpus {args.gpus}")
-    run_ours(args, wl)
+    run_ours(args)
 
 
 if __name__ == "__main__":

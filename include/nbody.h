@@ -108,6 +108,10 @@ typedef struct nbody_stats {
   float root_mass;
   int32_t walk_groups;     /* BH: groups of the last build */
   int32_t let_points;      /* BH domain split: locally-essential points received from the peers in the last step */
+  int32_t equal_mass;      /* direct sum: 1 = all sources carry one mass, the 11-lane-op kernel runs (mass applied in K2) */
+  int32_t sort_passes;     /* BH: 8-bit radix passes of the last build (only the key levels the tree needs are sorted) */
+  int32_t migrated;        /* BH domain split: bodies this rank received from other ranks in the last step */
+  int32_t reserved[5];
 } nbody_stats;
 
 typedef struct nbody_sim nbody_sim; /* opaque handle: owns device buffers, stream, events, NCCL communicator */
@@ -208,6 +212,10 @@ int nbody_load_snapshot(nbody_sim* sim, const char* path);
 /* ---- multi-GPU plumbing --------------------------------------------------------------------------- */
 /* 128-byte ncclUniqueId; rank 0 creates it and the launcher broadcasts it to all ranks before nbody_create. */
 int nbody_comm_unique_id(uint8_t out128[128]);
+/* Id of a fresh LOOP-BACK group: `world` handles created with it IN ONE PROCESS (one host thread per handle, usually all on
+ * one GPU) form a communicator whose collectives are device-to-device copies - the domain-split Barnes-Hut path
+ * (migration + locally-essential-tree exchange) then runs its real code on a single-GPU box. Not a performance path. */
+int nbody_comm_loopback_id(uint8_t out128[128]);
 
 /* ---- measurement helpers -------------------------------------------------------------------------- */
 /* FP32 FMA-chain microbenchmark on `device`: sustained FFMA throughput in TFLOP/s (2 flops per FMA) and the

@@ -77,6 +77,28 @@ def lib():
     return _lib
 
 
+def _bind_actor(R):
+    R.ref_create.restype = C.c_void_p
+    R.ref_destroy.argtypes = [C.c_void_p]
+    R.ref_set_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    R.ref_get_particles.argtypes = [C.c_void_p, C.c_void_p]
+    R.ref_num.argtypes = [C.c_void_p]
+    R.ref_set_dt.argtypes = [C.c_void_p, C.c_float]
+    R.ref_get_dt.argtypes = [C.c_void_p]
+    R.ref_get_dt.restype = C.c_float
+    R.ref_set_show_octree.argtypes = [C.c_void_p, C.c_int]
+    R.ref_get_size.argtypes = [C.c_void_p]
+    R.ref_get_size.restype = C.c_float
+    R.ref_create_space_points.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_uint]
+    R.ref_clean_particles.argtypes = [C.c_void_p]
+    R.ref_compute_cube_size.argtypes = [C.c_void_p]
+    R.ref_create_octree.argtypes = [C.c_void_p]
+    R.ref_tick.argtypes = [C.c_void_p, C.c_int]
+    R.ref_tick.restype = C.c_double
+    R.ref_debug_draws.argtypes = [C.c_void_p, _fp, C.c_int]
+    R.ref_debug_draws.restype = C.c_int
+
+
 def have_ref() -> bool:
     build()
     return os.path.exists(_REF)
@@ -89,30 +111,12 @@ def ref():
         if not os.path.exists(_REF):
             raise RuntimeError("oracle/_ref/liboracle_ref.so is missing (build it where /root/reference exists)")
         R = C.CDLL(_REF)
-        R.ref_create.restype = C.c_void_p
-        R.ref_destroy.argtypes = [C.c_void_p]
-        R.ref_set_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-        R.ref_get_particles.argtypes = [C.c_void_p, C.c_void_p]
-        R.ref_num.argtypes = [C.c_void_p]
-        R.ref_set_dt.argtypes = [C.c_void_p, C.c_float]
-        R.ref_get_dt.argtypes = [C.c_void_p]
-        R.ref_get_dt.restype = C.c_float
-        R.ref_set_show_octree.argtypes = [C.c_void_p, C.c_int]
-        R.ref_get_size.argtypes = [C.c_void_p]
-        R.ref_get_size.restype = C.c_float
-        R.ref_create_space_points.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_uint]
-        R.ref_clean_particles.argtypes = [C.c_void_p]
-        R.ref_compute_cube_size.argtypes = [C.c_void_p]
-        R.ref_create_octree.argtypes = [C.c_void_p]
-        R.ref_tick.argtypes = [C.c_void_p, C.c_int]
-        R.ref_tick.restype = C.c_double
+        _bind_actor(R)
         R.ref_compute_forces.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int]
         R.ref_compute_forces.restype = C.c_double
         R.ref_integrate.argtypes = [C.c_void_p]
         R.ref_root.argtypes = [C.c_void_p, _fp, _fp, _fp, _fp]
         R.ref_root.restype = C.c_int
-        R.ref_debug_draws.argtypes = [C.c_void_p, _fp, C.c_int]
-        R.ref_debug_draws.restype = C.c_int
         R.ref_max_threads.restype = C.c_int
         _ref = R
     return _ref
@@ -144,12 +148,37 @@ def from_aos(p: np.ndarray):
 
 
 # ----------------------------------------------------------------------------- the real reference
-class RefSim:
-    """The reference's AOctreeSearch, verbatim (OctreeSearch.h:111-149)."""
+_ADAPTER = os.path.join(os.path.dirname(_HERE), "integration", "ue4", "libue4_adapter.so")
+_adapter = None
 
-    def __init__(self):
-        self._r = ref()
+
+def have_adapter() -> bool:
+    return os.path.exists(_ADAPTER)
+
+
+def adapter():
+    """The same C driver (oracle/ref_wrap.cpp) compiled against the GPU adapter actor integration/ue4/OctreeSearch.{h,cpp},
+    which forwards to libnbody_b200.so (Makefile target integration/ue4/libue4_adapter.so)."""
+    global _adapter
+    if _adapter is None:
+        if not os.path.exists(_ADAPTER):
+            raise RuntimeError(f"{_ADAPTER} is missing: run `make`")
+        A = C.CDLL(_ADAPTER)
+        _bind_actor(A)
+        A.ref_adapter_config.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int]
+        _adapter = A
+    return _adapter
+
+
+class RefSim:
+    """The reference's AOctreeSearch, verbatim (OctreeSearch.h:111-149) - or, with use_adapter=True, the adapter actor of
+    integration/ue4 driven through the very same calls."""
+
+    def __init__(self, use_adapter: bool = False, theta: float = 1.0, eps: float = 0.0, direct: bool = False, parity: bool = True):
+        self._r = adapter() if use_adapter else ref()
         self._h = C.c_void_p(self._r.ref_create())
+        if use_adapter:
+            self._r.ref_adapter_config(self._h, theta, eps, int(direct), int(parity))
 
     def close(self):
         if self._h:
@@ -234,6 +263,15 @@ class RefSim:
 
 def ref_max_threads() -> int:
     return ref().ref_max_threads()
+
+
+def host_threads() -> int:
+    """Cores this process may run on. Pass it explicitly to the *_forces / direct_* calls: torchrun exports
+    OMP_NUM_THREADS=1, which is what omp_get_max_threads() (ref_max_threads / max_threads) would report."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 # ----------------------------------------------------------------------------- the C restatement

@@ -4,6 +4,10 @@
 // they lie (/root/reference/Source/NBody/OctreeSearch.{h,cpp}, NBody.h) against oracle/shim; nothing is
 // copied. Output goes to oracle/_ref/liboracle_ref.so (see oracle/Makefile). Every entry point is a thin
 // forward to a public member of AOctreeSearch (OctreeSearch.h:111-149).
+//
+// The same wrapper also drives the GPU adapter actor (integration/ue4/OctreeSearch.{h,cpp}: AOctreeSearch forwarding to
+// libnbody_b200.so) when compiled with -DNBODY_B200_ADAPTER -I integration/ue4, so a test can put the CPU actor and the
+// GPU actor side by side through identical calls.
 #include "NBody.h"
 #include "OctreeSearch.h"
 #include <chrono>
@@ -24,7 +28,9 @@ extern "C" {
 void* ref_create() { return new AOctreeSearch(); }
 void ref_destroy(void* h) {
   AOctreeSearch* s = (AOctreeSearch*)h;
+#ifndef NBODY_B200_ADAPTER
   if (s->ParticleOctree) s->CleanParticles();
+#endif
   delete s;
 }
 int ref_sizeof_particle() { return (int)sizeof(FParticle); }
@@ -34,7 +40,11 @@ void ref_set_particles(void* h, const void* aos, int n) {
   AOctreeSearch* s = (AOctreeSearch*)h;
   s->Particles.SetNum(n);
   if (n > 0) memcpy(&s->Particles[0], aos, (size_t)n * sizeof(FParticle));
+#ifdef NBODY_B200_ADAPTER
+  s->PushParticles();   // the device copy follows the host array
+#else
   s->Initialized = true;
+#endif
 }
 int ref_num(void* h) { return ((AOctreeSearch*)h)->Particles.Num(); }
 void ref_get_particles(void* h, void* aos) {
@@ -63,6 +73,15 @@ double ref_tick(void* h, int nsteps) {
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+#ifdef NBODY_B200_ADAPTER
+// Adapter-only knobs: the constants the reference bakes in.
+void ref_adapter_config(void* h, float theta, float eps, int direct, int parity) {
+  AOctreeSearch* s = (AOctreeSearch*)h;
+  s->Theta = theta; s->Softening = eps; s->bDirectSum = direct != 0; s->bReferenceParity = parity != 0;
+}
+int ref_is_adapter() { return 1; }
+#else
+int ref_is_adapter() { return 0; }
 // Force walk with a caller-chosen Theta on the CURRENT tree (ParticleOctree is public, OctreeSearch.h:119,
 // and Theta is a parameter of Octree::ComputeForces, OctreeSearch.h:99). Theta = 0 is the reference's only
 // "direct sum". Targets [i0, i1). Calls for different targets are independent (each writes only its own
@@ -75,7 +94,7 @@ double ref_compute_forces(void* h, float theta, int i0, int i1, int nthreads) {
   auto t0 = std::chrono::steady_clock::now();
 #ifdef _OPENMP
   if (nthreads > 1) {
-#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
     for (int i = i0; i < i1; i++) {
       s->Particles[i].Acceleration = FVector::ZeroVector;
       root->ComputeForces(&s->Particles[i], theta);
@@ -114,6 +133,8 @@ int ref_root(void* h, float* origin3, float* half, float* mass, float* com3) {
   return 1;
 }
 
+#endif
+
 // What DrawOctreeBoxes emitted on the last Tick (OctreeSearch.cpp:36-45): kind 0 = box (centre, half
 // extent), kind 1 = point. Returns the number of records; fills up to cap records of 7 floats.
 int ref_debug_draws(void* h, float* out7, int cap) {
@@ -125,6 +146,15 @@ int ref_debug_draws(void* h, float* out7, int cap) {
     o[0] = (float)d.kind; o[1] = d.a.X; o[2] = d.a.Y; o[3] = d.a.Z; o[4] = d.b.X; o[5] = d.b.Y; o[6] = d.b.Z;
   }
   return n;
+}
+
+// Full Ticks (OctreeSearch.cpp:21-34) are single threaded by construction - that is how the actor runs inside UE.
+int ref_hw_threads() {
+#ifdef _OPENMP
+  return omp_get_num_procs();
+#else
+  return 1;
+#endif
 }
 
 int ref_max_threads() {

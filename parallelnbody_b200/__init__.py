@@ -6,8 +6,8 @@ mirror of the reference's simulation-class interface (``AOctreeSearch``,
 harness. There is no CPU fallback: without the built CUDA library (or without a B200) every compute call raises.
 """
 from .api import (NBodyError, OctreeSearch, PARTICLE_DTYPE, METHOD_DIRECT, METHOD_BARNES_HUT, lib_path, load_library,
-                  measure_fp32_peak, comm_unique_id, sort_pairs_u64)
+                  measure_fp32_peak, comm_unique_id, comm_loopback_id, sort_pairs_u64)
 from . import ic  # noqa: F401
 
 __all__ = ["NBodyError", "OctreeSearch", "PARTICLE_DTYPE", "METHOD_DIRECT", "METHOD_BARNES_HUT", "lib_path",
-           "load_library", "measure_fp32_peak", "comm_unique_id", "sort_pairs_u64", "ic"]
+           "load_library", "measure_fp32_peak", "comm_unique_id", "comm_loopback_id", "sort_pairs_u64", "ic"]

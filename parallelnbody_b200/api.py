@@ -48,7 +48,8 @@ class Stats(C.Structure):
                 ("ms_last_call", C.c_float), ("ms_force", C.c_float), ("ms_build", C.c_float),
                 ("ms_integrate", C.c_float), ("ms_comm", C.c_float), ("cube_size", C.c_float), ("jsplit", C.c_int32),
                 ("i_per_thread", C.c_int32), ("tree_nodes", C.c_int32), ("tree_depth", C.c_int32),
-                ("root_com", C.c_float * 3), ("root_mass", C.c_float), ("walk_groups", C.c_int32), ("let_points", C.c_int32)]
+                ("root_com", C.c_float * 3), ("root_mass", C.c_float), ("walk_groups", C.c_int32), ("let_points", C.c_int32),
+                ("equal_mass", C.c_int32), ("sort_passes", C.c_int32), ("migrated", C.c_int32), ("reserved", C.c_int32 * 5)]
 
     def as_dict(self):
         d = {}
@@ -65,7 +66,7 @@ EXPORTS = [
     "nbody_synchronize", "nbody_get_particles_aos", "nbody_get_positions", "nbody_get_velocities",
     "nbody_get_accelerations", "nbody_get_local_ids", "nbody_set_param", "nbody_get_param", "nbody_energy",
     "nbody_stats_get", "nbody_octree_boxes", "nbody_device_ptrs", "nbody_comm_unique_id", "nbody_measure_fp32_peak",
-    "nbody_octree_nodes", "nbody_sort_pairs_u64", "nbody_save_snapshot", "nbody_load_snapshot",
+    "nbody_octree_nodes", "nbody_sort_pairs_u64", "nbody_save_snapshot", "nbody_load_snapshot", "nbody_comm_loopback_id",
 ]
 
 _lib = None
@@ -112,6 +113,7 @@ def load_library():
     L.nbody_octree_boxes.argtypes = [vp, vp, i64, C.POINTER(i64)]
     L.nbody_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.nbody_comm_unique_id.argtypes = [vp]
+    L.nbody_comm_loopback_id.argtypes = [vp]
     L.nbody_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.nbody_save_snapshot.argtypes = [vp, C.c_char_p]
     L.nbody_load_snapshot.argtypes = [vp, C.c_char_p]
@@ -149,6 +151,13 @@ def sort_pairs_u64(keys: np.ndarray, key_bits: int = 64, device: int = 0, timed:
 def comm_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()
     _check(load_library().nbody_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_loopback_id() -> bytes:
+    """Id of a fresh in-process (loop-back) group: create `world` handles with it, one host thread each."""
+    buf = (C.c_uint8 * 128)()
+    _check(load_library().nbody_comm_loopback_id(buf))
     return bytes(buf)
 
 

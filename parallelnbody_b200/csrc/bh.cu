@@ -680,6 +680,7 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
   int levels = kMaxLevel;
   if (p.leaf_size > 1 && p.mac == kMacGroup && p.depth_hint > 0) levels = std::min(kMaxLevel, std::max(10, p.depth_hint + 4));
   m->sorted = radix_sort_pairs(m->sort, n, 3 * kMaxLevel, s, launches, 3 * (kMaxLevel - levels));
+  st.sort_passes_host = (3 * kMaxLevel + 7) / 8 - std::min(3 * (kMaxLevel - levels) / 8, (3 * kMaxLevel + 7) / 8 - 1);
   gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[m->sorted], n, posm_in, vel_in, ids_in, posm, vel, ids);
   const uint64_t* keys = m->sort.keys[m->sorted];
   if (p.group_size != 32 && p.group_size != 64 && p.group_size != 128) { set_error("Barnes-Hut: group_size must be 32, 64 or 128"); return -1; }
@@ -1044,7 +1045,9 @@ int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, f
   NB_TRY(comm->all_gather_bytes(m->samples + (size_t)world * kLetMsg, m->samples, (size_t)kLetMsg * 8, s));
   int pow2 = 1;
   while (pow2 < world * kLetSamples) pow2 <<= 1;
+  NB_CUDA(cudaFuncSetAttribute(let_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12));   // world 9..16: 48 KB + static
   let_splitters_kernel<<<1, 1024, (size_t)pow2 * 12, s>>>(m->samples, world, p.let_time_weight, m->splitters);
+  NB_CUDA(cudaGetLastError());
   *launches += 4;
   int sorted = 0;
   if (n > 0) {
@@ -1067,7 +1070,17 @@ int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, f
     rb[q] = (size_t)(theirs[rank + 1] - theirs[rank]); ro[q] = (size_t)total;
     total += (int64_t)rb[q];
   }
-  if (total > cap) { set_error("Barnes-Hut LET: a rank's domain outgrew its body buffers (" + std::to_string(total) + " > " + std::to_string(cap) + ")"); return -5; }
+  // every rank sees every rank's offsets and the buffers have the same size everywhere, so all ranks take this exit
+  // together (a rank-local return in front of the exchange would leave the others blocked in the collective)
+  for (int d = 0; d < world; d++) {
+    int64_t total_d = 0;
+    for (int q = 0; q < world; q++) total_d += off[(size_t)q * (world + 1) + d + 1] - off[(size_t)q * (world + 1) + d];
+    if (total_d > cap) {
+      set_error("Barnes-Hut LET: the domain of rank " + std::to_string(d) + " outgrew the body buffers (" + std::to_string(total_d) + " > " +
+                std::to_string(cap) + ")");
+      return -5;
+    }
+  }
   auto exchange = [&](const void* send, void* recv, size_t elem) -> int {
     size_t a[kMaxWorld], b[kMaxWorld], c2[kMaxWorld], d[kMaxWorld];
     for (int q = 0; q < world; q++) { a[q] = sb[q] * elem; b[q] = so[q] * elem; c2[q] = rb[q] * elem; d[q] = ro[q] * elem; }
@@ -1115,9 +1128,11 @@ int bh_let_exchange(BHState& local, BHState& let, Comm* comm, const BHParams& p,
   NB_CUDA(cudaStreamSynchronize(s));
   size_t sb[kMaxWorld], so[kMaxWorld], rb[kMaxWorld], ro[kMaxWorld];
   int64_t total = 0;
+  // cap_let is the same on every rank (it derives from the body capacity), so an overflow anywhere fails everywhere
+  for (size_t k = 0; k < cnt.size(); k++)
+    if (cnt[k] > m->cap_let) { set_error("Barnes-Hut LET: export list overflow (" + std::to_string(cnt[k]) + " > " + std::to_string(m->cap_let) + ")"); return -5; }
   for (int q = 0; q < world; q++) {
     const int mine = cnt[(size_t)rank * world + q], theirs = cnt[(size_t)q * world + rank];
-    if (mine > m->cap_let) { set_error("Barnes-Hut LET: export list overflow"); return -5; }
     sb[q] = (size_t)mine * 16; so[q] = (size_t)q * (size_t)m->cap_let * 16;
     rb[q] = (size_t)theirs * 16; ro[q] = (size_t)total * 16;
     total += theirs;

@@ -30,7 +30,7 @@ struct BHParams {
 };
 
 struct BHState {
-  int n_nodes_host = 0, depth_host = 0, n_groups_host = 0;
+  int n_nodes_host = 0, depth_host = 0, n_groups_host = 0, sort_passes_host = 0;
   float root_com_host[3] = {0, 0, 0};
   float root_mass_host = 0;
   float root_cube_host[4] = {0, 0, 0, 0};  // centre xyz, half-width

@@ -98,7 +98,9 @@ direct_scalar_kernel(const float4* __restrict__ src, const int chunk, const floa
 // ---- packed-fp32 (f32x2) interaction over two sources ------------------------------------------------
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
-template <bool EPS0>
+// EQM = all sources carry the same mass: the mass factor leaves the inner loop (w = inv^3, 11 FMA-pipe lane-ops per
+// interaction instead of 12) and is applied once per target by the consumer together with G.
+template <bool EPS0, bool EQM = false>
 __device__ __forceinline__ void interact2(const float2 X, const float2 Y, const float2 Z, const float2 M,
                                           const float2 nxi, const float2 nyi, const float2 nzi,
                                           const float2 eps2, float2& ax, float2& ay, float2& az) {
@@ -114,20 +116,31 @@ __device__ __forceinline__ void interact2(const float2 X, const float2 Y, const 
     inv.y = r2.y >= kTinyR2 ? inv.y : 0.f;
   }
   const float2 inv2 = __fmul2_rn(inv, inv);
-  const float2 minv = __fmul2_rn(M, inv);
-  const float2 w = __fmul2_rn(minv, inv2);
+  float2 w;
+  if (EQM) {
+    w = __fmul2_rn(inv, inv2);
+  } else {
+    const float2 minv = __fmul2_rn(M, inv);
+    w = __fmul2_rn(minv, inv2);
+  }
   ax = __ffma2_rn(w, dx, ax);
   ay = __ffma2_rn(w, dy, ay);
   az = __ffma2_rn(w, dz, az);
 }
 
+// Padding entries of the source array: so far away that r^2 overflows to +inf, rsqrt gives +0 and the pair contributes
+// exactly nothing - with or without a mass factor (zero-mass padding would not do for the equal-mass kernel).
+constexpr float kPadCoord = 3.0e19f;
+
 // TPB threads per CTA = sources per shared-memory tile (default 256); chunk must be a multiple of TPB.
-template <int I, bool EPS0, int MINB, int TPB = kDirectTPB>
+template <int I, bool EPS0, int MINB, int TPB = kDirectTPB, bool EQM = false>
 __global__ void __launch_bounds__(TPB, MINB)
 direct_packed_kernel(const float4* __restrict__ src, const int chunk, const float4* __restrict__ tgt,
                      const int n_tgt, const float eps2s, float4* __restrict__ partial, const int n_tgt_pad) {
   // SoA tile, double buffered: [buf][component][j]
-  __shared__ __align__(16) float tile[2][4][TPB];
+  constexpr int NC = EQM ? 3 : 4;
+  constexpr int UNR = EQM ? 2 : 4;   // deeper unrolling of the equal-mass loop spills at I = 8 (ptxas: 255 registers + 32 B stack)
+  __shared__ __align__(16) float tile[2][NC][TPB];
   const int t = threadIdx.x;
   const int i_base = blockIdx.x * (TPB * I);
   float2 nxi[I], nyi[I], nzi[I], ax[I], ay[I], az[I];
@@ -145,21 +158,23 @@ direct_packed_kernel(const float4* __restrict__ src, const int chunk, const floa
   float4 nxt = s[t];
   for (int tl = 0; tl < ntiles; tl++) {
     const int b = tl & 1;
-    tile[b][0][t] = nxt.x; tile[b][1][t] = nxt.y; tile[b][2][t] = nxt.z; tile[b][3][t] = nxt.w;
+    tile[b][0][t] = nxt.x; tile[b][1][t] = nxt.y; tile[b][2][t] = nxt.z;
+    if (!EQM) tile[b][NC - 1][t] = nxt.w;
     __syncthreads();
     if (tl + 1 < ntiles) nxt = s[(size_t)(tl + 1) * TPB + t];
-#pragma unroll 4
+#pragma unroll UNR
     for (int j = 0; j < TPB; j += 4) {
       const float4 X = *reinterpret_cast<const float4*>(&tile[b][0][j]);
       const float4 Y = *reinterpret_cast<const float4*>(&tile[b][1][j]);
       const float4 Z = *reinterpret_cast<const float4*>(&tile[b][2][j]);
-      const float4 M = *reinterpret_cast<const float4*>(&tile[b][3][j]);
+      float4 M = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!EQM) M = *reinterpret_cast<const float4*>(&tile[b][NC - 1][j]);
 #pragma unroll
       for (int k = 0; k < I; k++) {
-        interact2<EPS0>(f2(X.x, X.y), f2(Y.x, Y.y), f2(Z.x, Z.y), f2(M.x, M.y), nxi[k], nyi[k], nzi[k], eps2,
-                        ax[k], ay[k], az[k]);
-        interact2<EPS0>(f2(X.z, X.w), f2(Y.z, Y.w), f2(Z.z, Z.w), f2(M.z, M.w), nxi[k], nyi[k], nzi[k], eps2,
-                        ax[k], ay[k], az[k]);
+        interact2<EPS0, EQM>(f2(X.x, X.y), f2(Y.x, Y.y), f2(Z.x, Z.y), f2(M.x, M.y), nxi[k], nyi[k], nzi[k], eps2,
+                             ax[k], ay[k], az[k]);
+        interact2<EPS0, EQM>(f2(X.z, X.w), f2(Y.z, Y.w), f2(Z.z, Z.w), f2(M.z, M.w), nxi[k], nyi[k], nzi[k], eps2,
+                             ax[k], ay[k], az[k]);
       }
     }
   }

@@ -221,6 +221,22 @@ scatter_float4_kernel(const float4* __restrict__ in, const int32_t* __restrict__
   if (i < n) out[ids[i]] = in[i];
 }
 
+// out[0] = min, out[1] = max of the order-preserving keys of the masses (posm.w); initialise out = {~0, 0}.
+__global__ void __launch_bounds__(256)
+mass_range_kernel(const float4* __restrict__ posm, const int64_t n, uint32_t* __restrict__ out) {
+  uint32_t lo = ~0u, hi = 0u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t k = float_to_ordered(ld_stream(posm + i).w);
+    lo = min(lo, k); hi = max(hi, k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(out, lo); atomicMax(out + 1, hi); }
+}
+
 __global__ void fill_float4_kernel(float4* p, const int64_t n, const float4 v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

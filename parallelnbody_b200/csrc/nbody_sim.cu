@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,13 +58,23 @@ DirectPlan plan_direct(int64_t n_tgt, int64_t n_src) {
   p.i_per_thread = p.variant == 0 ? 8 : 2;
   const int itile = kDirectTPB * p.i_per_thread;
   p.n_itiles = (int)ceil_div(n_tgt, itile);
-  // enough CTAs that the last partial wave is a few percent of the run, but chunks of >= 512 sources
-  const int64_t want_ctas = (int64_t)kNumSMsB200 * 48;
-  int js = 1;
-  while ((int64_t)p.n_itiles * js < want_ctas && js < 128 && ceil_div(n_src, js * 2) >= 512) js *= 2;
-  p.jsplit = js;
-  p.chunk = (int)round_up(ceil_div(n_src, js), kDirectTJ);
-  p.n_src_pad = (int64_t)p.chunk * js;
+  // j-split: the grid (i-tiles x j-splits) runs in waves of `slots` CTAs; pick the split whose last wave is fullest and
+  // whose source padding is smallest. Every split costs one float4 partial plane of HBM traffic per target, so among
+  // splits within 0.3 % of the best the smallest wins (N = 1M on 148 SMs: 13 splits = 44.97 waves, not 16 = 55.35).
+  const int slots = sm_count() * (p.variant == 0 ? 1 : 3);
+  int best = 1;
+  double best_cost = 1e30;
+  for (int js = 1; js <= 64; js++) {
+    const int64_t chunk = round_up(ceil_div(n_src, js), kDirectTJ);
+    if (js > 1 && chunk < 512) break;
+    const int64_t ctas = (int64_t)p.n_itiles * js;
+    const double waves = (double)ctas / slots;
+    const double cost = std::ceil(waves) / waves * ((double)chunk * js / (double)std::max<int64_t>(n_src, 1)) + 0.02 / std::max(1.0, std::floor(waves));
+    if (cost < best_cost - 0.003) { best_cost = cost; best = js; }
+  }
+  p.jsplit = best;
+  p.chunk = (int)round_up(ceil_div(n_src, best), kDirectTJ);
+  p.n_src_pad = (int64_t)p.chunk * best;
   p.n_tgt_pad = round_up(n_tgt, 32);
   return p;
 }
@@ -104,9 +115,12 @@ struct nbody_sim {
 
   Comm* comm = nullptr;
   DirectPlan plan;
+  bool equal_mass = false;    // direct sum: every source has the same (finite, non-zero) mass -> 11-lane-op kernel
+  float body_mass = 0.f;
   BHState tree;       // Barnes-Hut: tree over the bodies held by this rank
   BHState tree_let;   // multi-GPU LET mode: tree over the points received from the peers
   int n_let = 0;
+  int n_migrated = 0;
 
   // timing of the last call
   float ms_call = 0, ms_force = 0, ms_build = 0, ms_integrate = 0, ms_comm = 0;
@@ -127,6 +141,9 @@ struct nbody_sim {
   int64_t load_begin() const { return bh() && !let_mode() ? 0 : slice_begin; }
   int64_t load_count() const { return bh() && !let_mode() ? n_global : n_local; }
   float4* posm_load() { return d_posm + (bh() ? 0 : slice_begin); }
+  // original index of local body 0 while the bodies still sit in the order they were set in (ids_identity): in the
+  // domain-split mode the arrays start at 0 but hold the global slice [slice_begin, slice_begin + n_local)
+  int64_t identity_begin() const { return let_mode() ? slice_begin : local_begin; }
 };
 
 namespace {
@@ -206,12 +223,12 @@ int publish_positions(nbody_sim* s) {
   const int64_t slot_end = s->local_begin + s->n_per;
   const int64_t pad0 = s->local_begin + s->n_local;
   if (slot_end > pad0) {
-    fill_float4_kernel<<<(unsigned)ceil_div(slot_end - pad0, 256), 256, 0, s->stream>>>(s->d_posm + pad0, slot_end - pad0, make_float4(0, 0, 0, 0));
+    fill_float4_kernel<<<(unsigned)ceil_div(slot_end - pad0, 256), 256, 0, s->stream>>>(s->d_posm + pad0, slot_end - pad0, make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f));
     s->launches++;
   }
   const int64_t gathered = s->n_per * s->cfg.world;
   if (total > gathered) {
-    fill_float4_kernel<<<(unsigned)ceil_div(total - gathered, 256), 256, 0, s->stream>>>(s->d_posm + gathered, total - gathered, make_float4(0, 0, 0, 0));
+    fill_float4_kernel<<<(unsigned)ceil_div(total - gathered, 256), 256, 0, s->stream>>>(s->d_posm + gathered, total - gathered, make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f));
     s->launches++;
   }
   NB_CUDA(cudaGetLastError());
@@ -219,11 +236,11 @@ int publish_positions(nbody_sim* s) {
   return 0;
 }
 
-template <int V, bool E0>
+template <int V, bool E0, bool EQM>
 void launch_direct_variant(const DirectPlan& p, const float4* src, const float4* tgt, int n_tgt, float eps2, float4* partial, cudaStream_t st) {
   dim3 grid(p.n_itiles, p.jsplit);
-  if (V == 0) direct_packed_kernel<8, E0, 1><<<grid, kDirectTPB, 0, st>>>(src, p.chunk, tgt, n_tgt, eps2, partial, (int)p.n_tgt_pad);
-  else direct_packed_kernel<2, E0, 3><<<grid, kDirectTPB, 0, st>>>(src, p.chunk, tgt, n_tgt, eps2, partial, (int)p.n_tgt_pad);
+  if (V == 0) direct_packed_kernel<8, E0, 1, kDirectTPB, EQM><<<grid, kDirectTPB, 0, st>>>(src, p.chunk, tgt, n_tgt, eps2, partial, (int)p.n_tgt_pad);
+  else direct_packed_kernel<2, E0, 3, kDirectTPB, EQM><<<grid, kDirectTPB, 0, st>>>(src, p.chunk, tgt, n_tgt, eps2, partial, (int)p.n_tgt_pad);
 }
 
 int launch_direct(nbody_sim* s) {
@@ -231,16 +248,43 @@ int launch_direct(nbody_sim* s) {
   const float eps2 = s->cfg.eps * s->cfg.eps;
   const float4* tgt = s->posm_local();
   const bool e0 = !(eps2 > 0.f);
-  if (s->plan.variant == 0) {
-    if (e0) launch_direct_variant<0, true>(s->plan, s->d_posm, tgt, (int)s->n_local, eps2, s->d_partial, s->stream);
-    else launch_direct_variant<0, false>(s->plan, s->d_posm, tgt, (int)s->n_local, eps2, s->d_partial, s->stream);
-  } else {
-    if (e0) launch_direct_variant<1, true>(s->plan, s->d_posm, tgt, (int)s->n_local, eps2, s->d_partial, s->stream);
-    else launch_direct_variant<1, false>(s->plan, s->d_posm, tgt, (int)s->n_local, eps2, s->d_partial, s->stream);
+  const int n = (int)s->n_local;
+  const int sel = (s->plan.variant == 0 ? 0 : 4) + (e0 ? 2 : 0) + (s->equal_mass ? 1 : 0);
+  switch (sel) {
+    case 0: launch_direct_variant<0, false, false>(s->plan, s->d_posm, tgt, n, eps2, s->d_partial, s->stream); break;
+    case 1: launch_direct_variant<0, false, true>(s->plan, s->d_posm, tgt, n, eps2, s->d_partial, s->stream); break;
+    case 2: launch_direct_variant<0, true, false>(s->plan, s->d_posm, tgt, n, eps2, s->d_partial, s->stream); break;
+    case 3: launch_direct_variant<0, true, true>(s->plan, s->d_posm, tgt, n, eps2, s->d_partial, s->stream); break;
+    case 4: launch_direct_variant<1, false, false>(s->plan, s->d_posm, tgt, n, eps2, s->d_partial, s->stream); break;
+    case 5: launch_direct_variant<1, false, true>(s->plan, s->d_posm, tgt, n, eps2, s->d_partial, s->stream); break;
+    case 6: launch_direct_variant<1, true, false>(s->plan, s->d_posm, tgt, n, eps2, s->d_partial, s->stream); break;
+    default: launch_direct_variant<1, true, true>(s->plan, s->d_posm, tgt, n, eps2, s->d_partial, s->stream); break;
   }
   s->launches++;
   NB_CUDA(cudaGetLastError());
   s->interactions = (double)s->n_local * (double)s->n_global;
+  return 0;
+}
+
+// Direct sum: do all N sources carry one mass? (Reduced over the gathered source array, so every rank decides alike.)
+int detect_equal_mass(nbody_sim* s) {
+  s->equal_mass = false;
+  s->body_mass = 0.f;
+  if (s->cfg.method != NBODY_DIRECT || s->n_global <= 0) return 0;
+  if (getenv("NBODY_NO_EQUAL_MASS")) return 0;   // development knob: always the general kernel
+  static const uint32_t init[2] = {~0u, 0u};
+  uint32_t* d_mm = s->d_box;   // scratch: 2 words (min, max of the order-preserving mass keys)
+  NB_CUDA(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+  const int blocks = (int)std::min<int64_t>(ceil_div(s->n_global, 256), sm_count() * 8);
+  mass_range_kernel<<<blocks, 256, 0, s->stream>>>(s->d_posm, s->n_global, d_mm);
+  s->launches++;
+  NB_CUDA(cudaGetLastError());
+  uint32_t h[2];
+  NB_CUDA(cudaMemcpyAsync(h, d_mm, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+  NB_CUDA(cudaStreamSynchronize(s->stream));
+  const float lo = ordered_to_float(h[0]), hi = ordered_to_float(h[1]);
+  if (h[0] == h[1] && std::isfinite(lo) && lo != 0.f) { s->equal_mass = true; s->body_mass = lo; }
+  (void)hi;
   return 0;
 }
 
@@ -275,10 +319,11 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
     if (ev) NB_CUDA(cudaEventRecord(ev[2], s->stream));
     if (s->n_local > 0) {
       const unsigned blocks = (unsigned)ceil_div(s->n_local, 256);
+      const float gscale = s->equal_mass ? s->cfg.G * s->body_mass : s->cfg.G;   // equal-mass kernel leaves the mass to K2
       if (integrate)
-        reduce_kick_drift_kernel<true><<<blocks, 256, 0, s->stream>>>(s->d_partial, s->plan.jsplit, s->plan.n_tgt_pad, (int)s->n_local, s->cfg.G, dt, s->posm_local(), s->d_vel, s->d_acc);
+        reduce_kick_drift_kernel<true><<<blocks, 256, 0, s->stream>>>(s->d_partial, s->plan.jsplit, s->plan.n_tgt_pad, (int)s->n_local, gscale, dt, s->posm_local(), s->d_vel, s->d_acc);
       else
-        reduce_kick_drift_kernel<false><<<blocks, 256, 0, s->stream>>>(s->d_partial, s->plan.jsplit, s->plan.n_tgt_pad, (int)s->n_local, s->cfg.G, dt, s->posm_local(), s->d_vel, s->d_acc);
+        reduce_kick_drift_kernel<false><<<blocks, 256, 0, s->stream>>>(s->d_partial, s->plan.jsplit, s->plan.n_tgt_pad, (int)s->n_local, gscale, dt, s->posm_local(), s->d_vel, s->d_acc);
       s->launches++;
       NB_CUDA(cudaGetLastError());
     }
@@ -490,6 +535,7 @@ int finish_set(nbody_sim* s) {
   s->n_let = 0;
   s->walk_timed = false;
   NB_TRY(publish_positions(s));
+  NB_TRY(detect_equal_mass(s));
   NB_CUDA(cudaStreamSynchronize(s->stream));
   s->initialized = true;
   s->steps = 0;
@@ -506,7 +552,7 @@ int get_array(nbody_sim* s, int what, float* out4, int64_t n) {
   const float4* src = what == 0 ? s->posm_local() : what == 1 ? s->vel_local() : s->acc_local();
   if (s->n_local == 0) return 0;
   if (s->ids_identity) {
-    NB_CUDA(cudaMemcpyAsync(out4 + 4 * s->local_begin, src, (size_t)s->n_local * 16, cudaMemcpyDeviceToHost, s->stream));
+    NB_CUDA(cudaMemcpyAsync(out4 + 4 * s->identity_begin(), src, (size_t)s->n_local * 16, cudaMemcpyDeviceToHost, s->stream));
     NB_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
   }
@@ -560,6 +606,11 @@ int nbody_config_default(nbody_config* cfg) {
 int nbody_comm_unique_id(uint8_t out128[128]) {
   if (!out128) return invalid("out128 is NULL");
   return Comm::unique_id(out128);
+}
+
+int nbody_comm_loopback_id(uint8_t out128[128]) {
+  if (!out128) return invalid("out128 is NULL");
+  return Comm::loopback_id(out128);
 }
 
 int nbody_create(nbody_sim** out, const nbody_config* cfg) {
@@ -667,7 +718,14 @@ int nbody_set_bodies(nbody_sim* s, const float* posm4, const float* vel4, int64_
     else NB_CUDA(cudaMemsetAsync(s->d_vel, 0, bytes, s->stream));
     NB_CUDA(cudaMemsetAsync(s->d_acc, 0, bytes, s->stream));
     // an emulated rank has no communicator to gather the other slices: take all sources from the caller
-    if (s->emulated && !s->bh()) NB_CUDA(cudaMemcpyAsync(s->d_posm, posm4, (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
+    if (s->emulated && !s->bh()) {
+      NB_CUDA(cudaMemcpyAsync(s->d_posm, posm4, (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
+      // no all-gather will ever fill the padding of the other ranks' slots
+      if (s->cap_posm > n) {
+        fill_float4_kernel<<<(unsigned)ceil_div(s->cap_posm - n, 256), 256, 0, s->stream>>>(s->d_posm + n, s->cap_posm - n, make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f));
+        s->launches++;
+      }
+    }
   }
   return finish_set(s);
 }
@@ -749,7 +807,7 @@ int nbody_get_particles_aos(nbody_sim* s, void* particles, int64_t n, size_t str
   NB_CUDA(cudaGetLastError());
   uint8_t* dst = (uint8_t*)particles;
   if ((s->ids_identity || unpermute) && stride == 40) {
-    NB_CUDA(cudaMemcpyAsync(dst + (size_t)s->local_begin * 40, s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
+    NB_CUDA(cudaMemcpyAsync(dst + (size_t)(unpermute ? 0 : s->identity_begin()) * 40, s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
     NB_CUDA(cudaStreamSynchronize(s->stream));
     return NBODY_OK;
   }
@@ -762,7 +820,7 @@ int nbody_get_particles_aos(nbody_sim* s, void* particles, int64_t n, size_t str
   }
   NB_CUDA(cudaStreamSynchronize(s->stream));
   for (int64_t i = 0; i < s->n_local; i++) {
-    const int64_t g = (s->ids_identity || unpermute) ? s->local_begin + i : ids[(size_t)i];
+    const int64_t g = unpermute ? i : s->ids_identity ? s->identity_begin() + i : ids[(size_t)i];
     memcpy(dst + (size_t)g * stride, tmp.data() + (size_t)i * 40, 40);
   }
   return NBODY_OK;
@@ -775,7 +833,7 @@ int nbody_get_local_ids(nbody_sim* s, int64_t* ids, int64_t cap, int64_t* n_loca
   if (!ids) return NBODY_OK;
   if (cap < s->n_local) return invalid("ids capacity too small");
   if (s->ids_identity) {
-    for (int64_t i = 0; i < s->n_local; i++) ids[i] = s->local_begin + i;
+    for (int64_t i = 0; i < s->n_local; i++) ids[i] = s->identity_begin() + i;
     return NBODY_OK;
   }
   NB_CUDA(cudaSetDevice(s->cfg.device));
@@ -859,6 +917,9 @@ int nbody_stats_get(nbody_sim* s, nbody_stats* out) {
   out->cube_size = s->cube_size;
   out->jsplit = s->plan.jsplit; out->i_per_thread = s->plan.i_per_thread;
   out->tree_nodes = s->tree.n_nodes_host; out->tree_depth = s->tree.depth_host; out->walk_groups = s->tree.n_groups_host; out->let_points = s->n_let;
+  out->equal_mass = s->equal_mass ? 1 : 0;
+  out->sort_passes = s->tree.sort_passes_host;
+  out->migrated = s->n_migrated;
   memcpy(out->root_com, s->tree.root_com_host, sizeof(out->root_com));
   out->root_mass = s->tree.root_mass_host;
   return NBODY_OK;

@@ -18,4 +18,13 @@ for kw in (dict(), dict(mac=1, leaf_size=1, reference_root=True), dict(group_siz
 with P.OctreeSearch(method=P.METHOD_BARNES_HUT, theta=0.5) as s:
     s.SetBodies(posm[:1]); s.Tick(); s.SetBodies(posm[:70]); s.Tick()
 k, i = P.sort_pairs_u64(np.random.default_rng(0).integers(0, 1 << 63, 10007, dtype=np.uint64), 63)
+# domain-split Barnes-Hut (migration + LET exchange + second walk) over the loop-back communicator: 3 ranks, one thread each
+from concurrent.futures import ThreadPoolExecutor
+posm, vel = ic.two_galaxies(9001, seed=3)
+uid = P.comm_loopback_id()
+def rank_fn(r):
+    with P.OctreeSearch(method=P.METHOD_BARNES_HUT, eps=0.01, theta=0.35, rank=r, world=3, nccl_unique_id=uid, bh_exchange=0) as s:
+        s.SetBodies(posm, vel); s.Step(0.02, 3); s.Energy(); s.Positions(); return s.Stats()["let_points"]
+with ThreadPoolExecutor(3) as ex:
+    print("let points", list(ex.map(rank_fn, range(3))))
 print("sanitize probe done")
