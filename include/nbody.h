@@ -67,11 +67,11 @@ typedef struct nbody_config {
   int32_t leaf_size;      /* Barnes-Hut: max bodies per leaf bucket (default 16; 1 = reference's one-body leaves) */
   int32_t reference_root; /* Barnes-Hut: 1 = root cube as the reference (origin = previous root COM, half-width =
                              max |coord|, OctreeSearch.cpp:47-56,77-79); 0 = tight cube around the bodies */
-  int32_t mac;            /* Barnes-Hut acceptance test: 0 = per walk group of <= 64 neighbouring bodies (production: a cell
+  int32_t mac;            /* Barnes-Hut acceptance test: 0 = per walk group of <= group_size neighbouring bodies (production: a cell
                              is accepted when half-width / distance(group box, cell COM) < theta - never accepts what the
                              reference's per-body test would open); 1 = per body, exactly OctreeSearch.h:100-107 incl. the
                              visiting order (parity mode, slower) */
-  int32_t group_size;     /* Barnes-Hut (mac = 0): bodies per walk group, 32 / 64 / 128 (default 64) */
+  int32_t group_size;     /* Barnes-Hut (mac = 0): bodies per walk group, 32 / 64 / 128 (default 32) */
   int32_t group_pack;     /* Barnes-Hut (mac = 0): tree cells of <= group_pack * group_size bodies are cut into equal walk
                              groups (default 2; larger = fuller lanes, looser group boxes) */
   int32_t bh_exchange;    /* multi-GPU Barnes-Hut: 0 = Morton domain split, body migration and locally-essential-tree exchange

@@ -176,7 +176,7 @@ class OctreeSearch:
     def __init__(self, method: int = METHOD_BARNES_HUT, G: float = 1e4, eps: float = 0.0, theta: float = 1.0,
                  PhDeltaTime: float = 0.01, device: int = 0, rank: int = 0, world: int = 1,
                  nccl_unique_id: bytes | None = None, leaf_size: int = 16, reference_root: bool = False,
-                 mac: int = 0, group_size: int = 64, group_pack: int = 2, bh_exchange: int = -1, stream: int | None = None):
+                 mac: int = 0, group_size: int = 32, group_pack: int = 2, bh_exchange: int = -1, stream: int | None = None):
         self._L = load_library()
         cfg = _Config()
         _check(self._L.nbody_config_default(C.byref(cfg)))

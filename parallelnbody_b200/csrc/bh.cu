@@ -30,14 +30,16 @@ namespace {
 
 constexpr int kMaxLevel = 21;            // 3 * 21 = 63 key bits
 constexpr int kLeafFlag = 1 << 8;
-constexpr int kBodyFlag = 1 << 30;       // walk-stack entry is a body index, not a node
 // walk groups hold <= group_size bodies (32 * B, B bodies per lane, B in {1, 2, 4})
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
-constexpr int kWalkMinCtas = 4;          // register budget: 64 per thread -> 32 warps per SM; measured equal to 80 regs x 3 CTAs, and it leaves
-                                         // room for another stream's small kernels when the LET exchange runs beside a 3-CTA walk
-constexpr int kStackCap = 8192;          // per-warp walk stack entries (HBM/L2 resident)
-constexpr int kListCap = 64;             // per-warp interaction ring in shared memory
+constexpr int kWalkMinCtas = 3;          // register budget: 80 per thread -> 24 warps per SM (64 registers spill the streamed-leaf walk)
+constexpr int kStackCap = 8192;          // per-warp spill slab of the walk stack (HBM/L2 resident; cells only, rarely touched)
+constexpr int kStackSmem = 512;          // per-warp stack window in shared memory
+constexpr int kStackMask = kStackSmem - 1;
+constexpr int kListCap = 128;            // per-warp interaction ring in shared memory
+constexpr int kFlush = 64;               // pending entries evaluated per flush (the ring also holds up to 32 more + 31 left over)
+constexpr int kLeafChunk = 1 << 16;      // leaves at least this large are streamed on their own (bounds the packed scan of the walk)
 constexpr int kLetSamples = 256;         // key samples per rank for the domain splitters
 constexpr int kLetBoxes = 64;            // boxes describing a rank's domain to its peers
 constexpr int kMaxWorld = 16;
@@ -58,6 +60,7 @@ struct Impl {
   int2* node_range = nullptr;
   uint32_t* node_ready = nullptr;
   int2* groups = nullptr;            // walk groups: body ranges of <= group_size neighbours
+  int* group_cost = nullptr;         // interaction-list length of each group in the last walk (work measure for the domain split)
   Counters* counters = nullptr;
   float4* root = nullptr;          // [0] = cube (centre, half-width); [1] = previous root COM (xyz) + valid flag (w)
   int* stacks = nullptr;
@@ -117,6 +120,7 @@ int ensure(Impl* m, int n, cudaStream_t s) {
   NB_TRY(realloc_dev(&m->node_range, nodes));
   NB_TRY(realloc_dev(&m->node_ready, nodes));
   NB_TRY(realloc_dev(&m->groups, c));
+  NB_TRY(realloc_dev(&m->group_cost, c));
   m->cap_nodes = (int64_t)nodes;
   m->cap_n = (int64_t)c;
   return 0;
@@ -375,21 +379,23 @@ monopole_kernel(const float4* __restrict__ posm, const int2* __restrict__ range,
 }
 
 // ---- K8a: warp-coherent group walk ----------------------------------------------------------------------------
-// One warp per group of <= 64 Morton-neighbouring bodies (2 per lane, in registers). The warp pops up to 32 stack
+// One warp per group of <= group_size Morton-neighbouring bodies (B = 1, 2 or 4 per lane, in registers). The warp pops up to 32 stack
 // entries per round, one per lane; each lane tests its cell against the GROUP's bounding box:
 //     accept  <=>  half-width / dmin < theta,  dmin = distance(box, cell COM)          (cf. Size / d < Theta, h:103)
 // dmin <= every member's own d, so an accepted cell is one the reference would accept for each member. Accepted cells
 // and the bodies of opened leaves are appended to a 64-entry ring in shared memory; whenever 32 are pending, all lanes
 // evaluate them against their bodies with the direct-sum interaction (FP32-pipe bound, no divergence). Opened cells
-// push their children. The stack lives in a per-warp slab of global memory (L2 resident, coalesced).
+// push their children; the bodies of opened leaves never touch the stack - they are streamed through the ring 32 at a
+// time, the next chunk in flight while the current one is evaluated. The stack holds cells only: its top lives in shared
+// memory (512 entries per warp), older entries spill to a per-warp slab in global memory.
 // The pending ring is SoA (x[64] | y[64] | z[64] | m[64]) so that one LDS.128 yields four consecutive x (y, z, m) and the
 // evaluation runs on PAIRS of entries with Blackwell packed fp32 (FADD2 / FFMA2 / FMUL2), as K1 does.
 template <int B, bool EPS0>
-__device__ __forceinline__ void eval_list(const float* __restrict__ ring, const int head, const float2 (&nx)[B],
+__device__ __forceinline__ void eval_list(const float* __restrict__ ring, const int head, const int count, const float2 (&nx)[B],
                                           const float2 (&ny)[B], const float2 (&nz)[B], const float2 eps2,
                                           float2 (&ax)[B], float2 (&ay)[B], float2 (&az)[B]) {
 #pragma unroll 2
-  for (int j = 0; j < 32; j += 4) {
+  for (int j = 0; j < count; j += 4) {
     const float4 X = *reinterpret_cast<const float4*>(ring + head + j);
     const float4 Y = *reinterpret_cast<const float4*>(ring + kListCap + head + j);
     const float4 Z = *reinterpret_cast<const float4*>(ring + 2 * kListCap + head + j);
@@ -407,13 +413,18 @@ __global__ void __launch_bounds__(kWalkThreads, B <= 2 ? kWalkMinCtas : 2)
 bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com, const int4* __restrict__ node_meta,
                      const float4* __restrict__ tgt, const int2* __restrict__ groups, Counters* __restrict__ c,
                      const float4* __restrict__ root, const float theta2, const float eps2, const float G, const int t0,
-                     const int t1, const int accumulate, int* __restrict__ stacks, float4* __restrict__ acc) {
+                     const int t1, const int accumulate, int* __restrict__ stacks, float4* __restrict__ acc,
+                     int* __restrict__ group_cost) {
   // posm / node_* = the SOURCE tree; tgt / groups / c = the targets and their walk groups (the same tree, or - for
   // the locally-essential points received from other ranks - the local tree whose bodies are being accelerated)
   __shared__ __align__(16) float ring_all[kWalkWarps][4 * kListCap];
+  __shared__ int stk_all[kWalkWarps][kStackSmem];   // top of the warp's cell stack; older entries spill to the global slab
+  __shared__ int offs_all[kWalkWarps][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* ring = ring_all[w];
-  int* stack = stacks + (size_t)(blockIdx.x * kWalkWarps + w) * kStackCap;
+  int* stk = stk_all[w];
+  int* offs = offs_all[w];
+  int* gstack = stacks + (size_t)(blockIdx.x * kWalkWarps + w) * kStackCap;
   const int ngroups = c->ngroups;
   const float root_half = root[0].w;
   const unsigned lt = (1u << lane) - 1u;
@@ -447,22 +458,46 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
     const float gcx = 0.5f * (lox + hix), gcy = 0.5f * (loy + hiy), gcz = 0.5f * (loz + hiz);
     const float ghx = 0.5f * (hix - lox), ghy = 0.5f * (hiy - loy), ghz = 0.5f * (hiz - loz);
 
-    int top = 1, head = 0, pending = 0;
-    if (lane == 0) stack[0] = 0;
+    // logical stack [0, top): entries [base, top) live in the shared-memory window (index & kStackMask), [0, base) in the slab
+    int top = 1, base = 0, head = 0, pending = 0;
+    int leaf_first = 0, leaf_excl = 0, ltotal = 0, lpos = 0;   // bodies of the leaves opened by the last round, being streamed
+    if (lane == 0) stk[0] = 0;
     __syncwarp();
     unsigned long long entries = 0;
-    while (top > 0) {
-      const int nb = min(32, top);
-      top -= nb;
-      const int e = lane < nb ? stack[top + lane] : -1;
-      float4 item = make_float4(0.f, 0.f, 0.f, 0.f);
-      bool has_item = false;
-      int push_first = 0, push_n = 0, push_flag = 0;
-      if (e >= 0) {
-        if (e & kBodyFlag) {
-          item = posm[e & ~kBodyFlag];
-          has_item = true;
-        } else {
+    bool overflow = false;
+    // One loop, one evaluation site. Each trip either streams the next 32 bodies of the opened leaves into the ring, or - when
+    // none are left - pops up to 32 cells, tests them and queues what they yield; kFlush pending entries are evaluated at once.
+    while (true) {
+      if (lpos < ltotal) {
+        // flat index j over all opened leaves of the round -> owner lane by binary search in the exclusive prefix of the sizes
+        const int j = lpos + lane;
+        int L = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) if (offs[L + step] <= j) L += step;
+        const int first = __shfl_sync(0xffffffffu, leaf_first, L), off = __shfl_sync(0xffffffffu, leaf_excl, L);
+        const int cnt = min(32, ltotal - lpos);
+        if (lane < cnt) {
+          const float4 bd = posm[first + (j - off)];
+          const int slot = (head + pending + lane) & (kListCap - 1);
+          ring[slot] = bd.x; ring[kListCap + slot] = bd.y; ring[2 * kListCap + slot] = bd.z; ring[3 * kListCap + slot] = bd.w;
+        }
+        pending += cnt;
+        lpos += 32;
+      } else if (top > 0) {
+        if (top == base) {   // window empty: bring the youngest spilled entries back
+          const int cnt = min(base, kStackSmem / 2);
+          for (int k = lane; k < cnt; k += 32) stk[(base - cnt + k) & kStackMask] = gstack[base - cnt + k];
+          base -= cnt;
+          __syncwarp();
+        }
+        const int nb = min(32, top - base);
+        top -= nb;
+        const int e = lane < nb ? stk[(top + lane) & kStackMask] : -1;
+        float4 item = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool has_item = false;
+        int push_first = 0, push_n = 0, leaf_n = 0;
+        leaf_first = 0;
+        if (e >= 0) {
           const float4 cm = node_com[e];
           const int4 m = node_meta[e];
           const bool leaf = (m.z & kLeafFlag) != 0;
@@ -471,45 +506,91 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
                       dz = fmaxf(fabsf(cm.z - gcz) - ghz, 0.f);
           const float dmin2 = dx * dx + dy * dy + dz * dz;
           if (size * size < theta2 * dmin2 || (leaf && m.y == 1)) { item = cm; has_item = true; }
-          else { push_first = m.x; push_n = m.y; push_flag = leaf ? kBodyFlag : 0; }
+          else if (leaf) { leaf_first = m.x; leaf_n = m.y; }
+          else { push_first = m.x; push_n = m.y; }
         }
-      }
-      // children / leaf bodies of the opened cells go on the stack
-      int incl = push_n;
+        // a leaf too large for the packed scan below (a deepest-level cell full of coincident bodies): stream it on its own
+        unsigned big = __ballot_sync(0xffffffffu, leaf_n >= kLeafChunk);
+        while (big) {
+          const int src = __ffs(big) - 1;
+          big &= big - 1;
+          const int f = __shfl_sync(0xffffffffu, leaf_first, src), n = __shfl_sync(0xffffffffu, leaf_n, src);
+          for (int b0 = 0; b0 < n; b0 += 32) {
+            const int cnt = min(32, n - b0);
+            if (lane < cnt) {
+              const float4 bd = posm[f + b0 + lane];
+              const int slot = (head + pending + lane) & (kListCap - 1);
+              ring[slot] = bd.x; ring[kListCap + slot] = bd.y; ring[2 * kListCap + slot] = bd.z; ring[3 * kListCap + slot] = bd.w;
+            }
+            pending += cnt;
+            __syncwarp();
+            if (pending >= 32) {
+              eval_list<B, EPS0>(ring, head, 32, nx, ny, nz, eps2v, ax, ay, az);
+              head = (head + 32) & (kListCap - 1);
+              pending -= 32;
+              entries += 32;
+              __syncwarp();
+            }
+          }
+          if (lane == src) leaf_n = 0;
+        }
+        // one warp scan for both counts: children to push (<= 8 per lane, low 10 bits) and leaf bodies to stream (high bits)
+        int incl = push_n | (leaf_n << 10);
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (top + total > kStackCap) { if (lane == 0) atomicExch(&c->overflow, 1); top = 0; pending = 0; break; }
-      int* dst = stack + top + incl - push_n;
-      for (int k = 0; k < push_n; k++) dst[k] = (push_first + k) | push_flag;
-      top += total;
-      // accepted cells / bodies join the pending interaction ring
-      const unsigned mask = __ballot_sync(0xffffffffu, has_item);
-      if (has_item) {
-        const int slot = (head + pending + __popc(mask & lt)) & (kListCap - 1);
-        ring[slot] = item.x; ring[kListCap + slot] = item.y; ring[2 * kListCap + slot] = item.z; ring[3 * kListCap + slot] = item.w;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int both = __shfl_sync(0xffffffffu, incl, 31);
+        const int total = both & 1023;
+        ltotal = both >> 10;
+        lpos = 0;
+        leaf_excl = (incl >> 10) - leaf_n;
+        if (ltotal) offs[lane] = leaf_excl;
+        if (total) {   // children of the opened cells go on the stack
+          const int need = (top - base) + total - kStackSmem;
+          if (need > 0) {   // make room: the oldest entries of the window move to the slab
+            const int sp = min((need + 31) & ~31, top - base);
+            if (base + sp > kStackCap) { overflow = true; break; }
+            for (int k = lane; k < sp; k += 32) gstack[base + k] = stk[(base + k) & kStackMask];
+            base += sp;
+            __syncwarp();
+          }
+          const int dst = top + (incl & 1023) - push_n;
+#pragma unroll
+          for (int k = 0; k < 8; k++) if (k < push_n) stk[(dst + k) & kStackMask] = push_first + k;
+          top += total;
+        }
+        // accepted cells join the pending interaction ring
+        const unsigned mask = __ballot_sync(0xffffffffu, has_item);
+        if (has_item) {
+          const int slot = (head + pending + __popc(mask & lt)) & (kListCap - 1);
+          ring[slot] = item.x; ring[kListCap + slot] = item.y; ring[2 * kListCap + slot] = item.z; ring[3 * kListCap + slot] = item.w;
+        }
+        pending += __popc(mask);
+      } else {
+        break;
       }
-      pending += __popc(mask);
       __syncwarp();
-      if (pending >= 32) {
-        eval_list<B, EPS0>(ring, head, nx, ny, nz, eps2v, ax, ay, az);
-        head = (head + 32) & (kListCap - 1);
-        pending -= 32;
-        entries += 32;
+      if (pending >= kFlush) {
+        eval_list<B, EPS0>(ring, head, kFlush, nx, ny, nz, eps2v, ax, ay, az);
+        head = (head + kFlush) & (kListCap - 1);
+        pending -= kFlush;
+        entries += kFlush;
         __syncwarp();
       }
     }
-    if (pending > 0) {  // tail: pad the ring with massless entries so the evaluation stays branch-free
-      if (lane >= pending) {
-        const int slot = (head + lane) & (kListCap - 1);
+    if (overflow) { if (lane == 0) atomicExch(&c->overflow, 1); pending = 0; }
+    if (pending > 0) {  // tail: pad the ring with massless entries up to a multiple of 4 so the evaluation stays branch-free
+      const int padded = (pending + 3) & ~3;
+      if (lane < padded - pending) {
+        const int slot = (head + pending + lane) & (kListCap - 1);
         ring[slot] = 0.f; ring[kListCap + slot] = 0.f; ring[2 * kListCap + slot] = 0.f; ring[3 * kListCap + slot] = 0.f;
       }
       __syncwarp();
-      eval_list<B, EPS0>(ring, head, nx, ny, nz, eps2v, ax, ay, az);
+      eval_list<B, EPS0>(ring, head, padded, nx, ny, nz, eps2v, ax, ay, az);
       entries += pending;
       __syncwarp();
     }
     inter += entries * (unsigned long long)ntarget;
+    if (group_cost && lane == 0) group_cost[g] = (accumulate ? group_cost[g] : 0) + (int)min(entries, 0x3fffffffull);
 #pragma unroll
     for (int k = 0; k < B; k++) {
       const int i = r.x + lane + 32 * k;
@@ -629,7 +710,7 @@ int launch_walk(Impl* m, Impl* g, const BHParams& p, const float4* posm, const f
   NB_CUDA(cudaMemsetAsync(&g->counters->next_group, 0, sizeof(int), s));
   bh_walk_group_kernel<B, EPS0><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, tgt, g->groups, g->counters, m->root,
                                                               p.theta * p.theta, p.eps2, p.G, t0, t1, accumulate ? 1 : 0,
-                                                              m->stacks, acc);
+                                                              m->stacks, acc, g->group_cost);
   return 0;
 }
 
@@ -651,7 +732,7 @@ void bh_free(BHState& st) {
   Impl* m = static_cast<Impl*>(st.impl);
   for (int k = 0; k < 2; k++) { cudaFree(m->sort.keys[k]); cudaFree(m->sort.idx[k]); }
   cudaFree(m->sort.hist); cudaFree(m->sort.tile_sums);
-  cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->groups);
+  cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->groups); cudaFree(m->group_cost);
   cudaFree(m->counters); cudaFree(m->root); cudaFree(m->stacks); cudaFree(m->boxes);
   cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_boxes); cudaFree(m->cut);
   cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->let_cnt); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);

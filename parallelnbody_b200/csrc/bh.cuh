@@ -10,7 +10,7 @@
 namespace nbody {
 
 enum BHMac : int {
-  kMacGroup = 0,  // one warp walks for a group of <= 64 neighbouring bodies; a cell is accepted when
+  kMacGroup = 0,  // one warp walks for a group of <= group_size neighbouring bodies; a cell is accepted when
                   // half-width / (distance from the group's bounding box to the cell's centre of mass) < theta.
                   // Never accepts a cell the reference's per-body test (OctreeSearch.h:103) would open.
   kMacBody = 1    // per body, exactly OctreeSearch.h:100-107: skip d == 0, accept when Size / d < Theta or one-body leaf,
@@ -22,7 +22,7 @@ struct BHParams {
   int leaf_size = 16;
   bool reference_root = false;
   int mac = kMacGroup;
-  int group_size = 64;  // bodies per walk group: 32, 64 or 128 (1, 2 or 4 per lane)
+  int group_size = 32;  // bodies per walk group: 32, 64 or 128 (1, 2 or 4 per lane)
   bool leave_sm_slot = false;  // walk with one CTA per SM fewer than fit, so kernels of another stream can run beside it
   float let_time_weight = 0.f; // domain split: 0 = equal body counts per rank, up to 1 = equal last-step walk time
   int depth_hint = 0;          // last known tree depth (0 = unknown): how many key levels the sort has to resolve

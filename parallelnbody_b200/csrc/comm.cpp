@@ -243,7 +243,9 @@ class LoopComm : public Comm {
     NB_TRY(loop_barrier(g_.get()));
     for (int p = 0; p < world_; p++)                        // nothing after this call may touch my send buffer before
       if (p != rank_) NB_CUDA(cudaStreamWaitEvent(s, g_->slot[p].done, 0));   // every peer has copied out of it
-    return 0;
+    // a rank may destroy its communicator (and these events) right after its last collective: nobody leaves before
+    // everybody has enqueued its waits
+    return loop_barrier(g_.get());
   }
   int all_gather_bytes(const void* send, void* recv, size_t bytes, cudaStream_t s) override {
     size_t sb[kLoopMaxWorld], so[kLoopMaxWorld], rb[kLoopMaxWorld], ro[kLoopMaxWorld];

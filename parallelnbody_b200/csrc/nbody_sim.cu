@@ -597,7 +597,7 @@ int nbody_config_default(nbody_config* cfg) {
   cfg->leaf_size = 16;
   cfg->reference_root = 0;
   cfg->mac = 0;
-  cfg->group_size = 64;
+  cfg->group_size = 32;   // measured (profiles/): 32-body groups, cells of <= 64 bodies cut in two, 16-body leaves = shortest step at N = 1M
   cfg->group_pack = 2;
   cfg->bh_exchange = -1;
   return NBODY_OK;

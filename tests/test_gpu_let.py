@@ -176,6 +176,7 @@ def test_loopback_direct_and_replicated_are_bit_identical(method, exchange):
     def rank_fn(r, uid):
         with P.OctreeSearch(method=meth, eps=eps, theta=0.3, rank=r, world=world, nccl_unique_id=uid, bh_exchange=exchange) as s:
             s.SetBodies(posm, vel)
+            s.CreateOctree()          # as _single does: the second build then sorts the same number of key levels
             s.Step(1e-3, 5)
             return s.LocalIds(), s.Positions(), s.Velocities()
 
