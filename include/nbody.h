@@ -163,13 +163,18 @@ int nbody_synchronize(nbody_sim* sim);
 /* ---- bodies out (replaces reading Particles[i].Position/Velocity/Acceleration, OctreeSearch.h:118) ---- */
 /* Each writes this rank's share into the GLOBAL-size output at the bodies' original indices; with world > 1
  * the caller combines ranks (shares are disjoint). `n` is the capacity of the output in bodies (>= n_global).
- * Barnes-Hut reorders the bodies along the Morton curve every step; the original indices travel with them. */
+ * Barnes-Hut reorders the bodies along the Morton curve every step; the original indices travel with them.
+ * Domain-split Barnes-Hut (bh_exchange = 0, world > 1): bodies migrate between ranks, so the read-backs (and the
+ * set_* calls, nbody_energy) are COLLECTIVES - every rank calls them together; each rank gets back the rows of its own
+ * slice of the caller's order, [rank * ceil(n / world), ...), returned to it by the ranks that hold those bodies now, in
+ * one contiguous copy. */
 int nbody_get_particles_aos(nbody_sim* sim, void* particles, int64_t n, size_t stride);
 int nbody_get_positions(nbody_sim* sim, float* posm4, int64_t n);
 int nbody_get_velocities(nbody_sim* sim, float* vel4, int64_t n);
 int nbody_get_accelerations(nbody_sim* sim, float* acc4, int64_t n);
-/* Which original body indices this rank currently owns: ids[n_local] (capacity cap). Direct sum: a fixed
- * contiguous slice; Barnes-Hut multi-GPU: changes as bodies migrate between domains. */
+/* The rows this rank's read-backs fill: ids[n_local] (capacity cap). Direct sum and domain-split Barnes-Hut: a fixed
+ * contiguous slice of the caller's order (the bodies a domain-split rank INTEGRATES change as they migrate: see
+ * nbody_stats.n_local / migrated); replicated-tree Barnes-Hut: the bodies of the rank's slice of the Morton order. */
 int nbody_get_local_ids(nbody_sim* sim, int64_t* ids, int64_t cap, int64_t* n_local);
 
 /* ---- parameters (replaces the Blueprint-exposed members PhDeltaTime / ShowOctree, OctreeSearch.h:123-127, and the

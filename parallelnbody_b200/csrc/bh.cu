@@ -43,6 +43,7 @@ constexpr int kLeafChunk = 1 << 16;      // leaves at least this large are strea
 constexpr int kLetSamples = 256;         // key samples per rank for the domain splitters
 constexpr int kLetBoxes = 64;            // boxes describing a rank's domain to its peers
 constexpr int kMaxWorld = 16;
+constexpr int kCostBins = 1024;          // equal-count bins along the sorted bodies in which the walks record their work
 
 struct Counters {
   int nnodes, ngroups, ticket, depth, next_group, overflow, pad0, pad1;
@@ -71,15 +72,19 @@ struct Impl {
   // --- multi-GPU domain decomposition + locally-essential-tree exchange (K9), allocated on first use
   int let_world = 0;
   uint64_t* samples = nullptr;     // [world * kLetSamples] gathered key samples
-  uint64_t* splitters = nullptr;   // [world - 1]
-  int* send_off = nullptr;         // [world + 1] body ranges per destination rank
-  int* all_off = nullptr;          // [world * (world + 1)] every rank's send_off / LET counts
+  uint64_t* splitters = nullptr;   // [world + 1] first key of every rank's domain (0 ... ~0)
+  int* send_off = nullptr;         // [2 world + 1] body ranges per destination rank | export counts per peer
+  int* all_off = nullptr;          // [world * (2 world + 1)] every rank's message
   float* peer_boxes = nullptr;     // [world * kLetBoxes * 6] (min xyz, max xyz) of each rank's domain cells
   int2* cut = nullptr;             // [kLetBoxes] body ranges of the local tree cells behind this rank's boxes
   uint32_t* visit = nullptr;       // per node: which peers still descend through it
   int64_t cap_visit = 0;
   float4* let_out = nullptr;       // [world * cap_let] per-peer export lists
-  int* let_cnt = nullptr;          // [world]
+  int* let_cnt = nullptr;          // [world] export counts (the tail of the send_off message, not an allocation of its own)
+  uint32_t* bin_cost = nullptr;    // [kCostBins] interactions evaluated for the bodies of each equal-count bin (last step)
+  bool splitters_valid = false;    // the splitters describe balanced domains of the system this handle last ran
+  float* ret = nullptr;            // read-back staging (return to owner)
+  int64_t cap_ret = 0;
   int64_t cap_let = 0;
   float4* let_in = nullptr;        // received points
   float4* let_sorted = nullptr;    // the same in Morton order (sources of the LET tree)
@@ -110,10 +115,9 @@ int ensure(Impl* m, int n, cudaStream_t s) {
   if (n <= m->cap_n) return 0;
   NB_CUDA(cudaStreamSynchronize(s));
   const size_t c = (size_t)n + (size_t)n / 8 + 1024;
-  const size_t nblocks = ceil_div((int64_t)c, kSortTile);
   for (int k = 0; k < 2; k++) { NB_TRY(realloc_dev(&m->sort.keys[k], c)); NB_TRY(realloc_dev(&m->sort.idx[k], c)); }
-  NB_TRY(realloc_dev(&m->sort.hist, 256 * nblocks));
-  NB_TRY(realloc_dev(&m->sort.tile_sums, ceil_div((int64_t)(256 * nblocks), kScanTile) + 1));
+  m->sort.work_words = radix_work_words((int64_t)c);
+  NB_TRY(realloc_dev(&m->sort.work, m->sort.work_words));
   const size_t nodes = 2 * c + 8;
   NB_TRY(realloc_dev(&m->node_com, nodes));
   NB_TRY(realloc_dev(&m->node_meta, nodes));
@@ -131,9 +135,9 @@ int ensure(Impl* m, int n, cudaStream_t s) {
 // max |coordinate| (OctreeSearch.cpp:47-56,77-79) - such a cube need not contain every body, exactly as in the
 // reference, where outliers are still routed by the octant comparisons; here their quantised coordinates clamp.
 // Otherwise: the tight bounding cube.
-__global__ void root_cube_kernel(const uint32_t* __restrict__ box, const int reference_root, float4* __restrict__ root) {
+__global__ void root_cube_kernel(const uint32_t* __restrict__ box, const int mode, float4* __restrict__ root) {
   float cx, cy, cz, half;
-  if (reference_root) {
+  if (mode == 1) {   // the reference's root
     const float4 prev = root[1];
     cx = prev.x; cy = prev.y; cz = prev.z;
     half = __uint_as_float(box[0]);
@@ -143,6 +147,15 @@ __global__ void root_cube_kernel(const uint32_t* __restrict__ box, const int ref
     cx = 0.5f * (lx + hx); cy = 0.5f * (ly + hy); cz = 0.5f * (lz + hz);
     half = 0.5f * fmaxf(fmaxf(hx - lx, hy - ly), hz - lz);
     half = half * 1.0001f + 1e-30f;
+    if (mode == 2) {
+      // sticky cube (multi-GPU domain split): keep the previous cube while it still holds every body and is not far too
+      // large, so that keys - and the domain splitters, which are keys - mean the same from step to step
+      const float4 prev = root[0];
+      const bool inside = prev.w > 0.f && lx >= prev.x - prev.w && hx <= prev.x + prev.w && ly >= prev.y - prev.w && hy <= prev.y + prev.w &&
+                          lz >= prev.z - prev.w && hz <= prev.z + prev.w;
+      if (inside && prev.w <= 3.f * half) return;
+      half *= 1.25f;
+    }
   }
   if (!(half > 0.f) || !isfinite(half)) half = 1.f;
   root[0] = make_float4(cx, cy, cz, half);
@@ -175,23 +188,36 @@ __device__ __forceinline__ uint32_t quantize(float x, float centre, float half) 
   return (uint32_t)fminf(fmaxf(f, 0.f), 2097151.f);
 }
 
+// ghist (may be NULL): histogram of the key digit at `shift` = what the first radix pass needs up front; counted here so the
+// sort never re-reads the keys for it.
 __global__ void __launch_bounds__(256)
-morton_kernel(const float4* __restrict__ posm, const int n, const float4* __restrict__ root, uint64_t* __restrict__ keys) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+morton_kernel(const float4* __restrict__ posm, const int n, const float4* __restrict__ root, uint64_t* __restrict__ keys,
+              uint32_t* __restrict__ ghist, const int shift, const BodySegs segs = BodySegs{0, 0x7fffffff, 0}) {
+  __shared__ uint32_t h[256];
+  if (ghist) { h[threadIdx.x] = 0; __syncthreads(); }
   const float4 c = root[0];
-  const float4 p = ld_stream(posm + i);
-  const uint32_t qx = quantize(p.x, c.x, c.w), qy = quantize(p.y, c.y, c.w), qz = quantize(p.z, c.z, c.w);
-  keys[i] = expand21(qx) << 2 | expand21(qy) << 1 | expand21(qz);   // octant digit = 4*X + 2*Y + Z (OctreeSearch.h:50-56)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = ld_stream(posm + segs.at(i));
+    const uint32_t qx = quantize(p.x, c.x, c.w), qy = quantize(p.y, c.y, c.w), qz = quantize(p.z, c.z, c.w);
+    const uint64_t k = expand21(qx) << 2 | expand21(qy) << 1 | expand21(qz);   // octant digit = 4*X + 2*Y + Z (OctreeSearch.h:50-56)
+    keys[i] = k;
+    if (ghist) atomicAdd(&h[(uint32_t)(k >> shift) & 255u], 1u);
+  }
+  if (ghist) {
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(ghist + threadIdx.x, h[threadIdx.x]);
+  }
 }
 
+// order[i] = logical input index of the i-th sorted body; segs maps logical indices to storage (the bodies that stayed on
+// this rank, then the ones that arrived: see bh_let_finish).
 __global__ void __launch_bounds__(256)
-gather_bodies_kernel(const uint32_t* __restrict__ order, const int n, const float4* __restrict__ posm_in,
+gather_bodies_kernel(const uint32_t* __restrict__ order, const int n, const BodySegs segs, const float4* __restrict__ posm_in,
                      const float4* __restrict__ vel_in, const int32_t* __restrict__ ids_in, float4* __restrict__ posm_out,
                      float4* __restrict__ vel_out, int32_t* __restrict__ ids_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t j = order[i];
+  const int j = segs.at((int)order[i]);
   st_stream(posm_out + i, posm_in[j]);
   if (vel_in) st_stream(vel_out + i, vel_in[j]);
   if (ids_in) ids_out[i] = ids_in[j];
@@ -243,11 +269,16 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
   const unsigned gmask = 0xffu << gshift;
   const int stride = gridDim.x * blockDim.x / 8;
   int maxlvl = 0;
-  for (int node = gb + (blockIdx.x * blockDim.x + threadIdx.x) / 8; node < ge; node += stride) {
-    const int2 r = range[node];
-    const int4 m = meta[node];
+  // a warp takes 4 consecutive nodes per trip (8 lanes each); the trip count is uniform over the warp
+  for (int node0 = gb + (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / 8; node0 < ge; node0 += stride) {
+    const int node = node0 + (lane >> 3);
+    const bool live = node < ge;
+    int2 r = make_int2(0, 0);
+    int4 m = make_int4(0, 0, 0, -1);
+    if (live) { r = range[node]; m = meta[node]; }
     const int cnt = r.y - r.x, level = m.z;
-    if (cnt <= leaf_size || level >= levels) {
+    const bool split = live && cnt > leaf_size && level < levels;
+    if (live && !split) {
       if (sub == 0) {
         meta[node] = make_int4(r.x, cnt, level | kLeafFlag, m.w);
         // > super bodies in one deepest-level cell (coincident to the key resolution): walk them in chunks
@@ -256,12 +287,11 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
       int d = m.w >= 0 ? (meta[m.w].z & 255) + 1 : 0;   // depth of the leaf's cell in the reference's tree
       if (cnt > leaf_size && level < kMaxLevel) d = levels + 1;   // the sort was too shallow for this cell: ask for more next time
       maxlvl = max(maxlvl, d);
-      continue;
     }
-    const int shift = 3 * (kMaxLevel - 1 - level);
+    const int shift = 3 * (kMaxLevel - 1 - min(level, kMaxLevel - 1));
     // first body whose digit at this level is >= sub: 8-ary search (7 independent probes per round, so the chain of
     // dependent L2 round trips is log8 of the range), then a binary search on the last few bodies
-    int lo = r.x, hi = r.y;
+    int lo = r.x, hi = split ? r.y : r.x;
     while (hi - lo > 16) {
       const int w = (hi - lo) >> 3;
       int d[7];
@@ -282,15 +312,20 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
       const int mid = (lo + hi) >> 1;
       if ((int)((keys[mid] >> shift) & 7ull) < sub) lo = mid + 1; else hi = mid;
     }
+    __syncwarp();
     const int start = lo;
-    int next = __shfl_down_sync(gmask, start, 1, 8);
+    int next = __shfl_down_sync(0xffffffffu, start, 1, 8);
     if (sub == 7) next = r.y;
-    const int cc = next - start;
-    const unsigned nonempty = (__ballot_sync(gmask, cc > 0) >> gshift) & 0xffu;
+    const int cc = split ? next - start : 0;
+    const unsigned nonempty = (__ballot_sync(0xffffffffu, cc > 0) >> gshift) & 0xffu;
     const int nchild = __popc(nonempty), slot = __popc(nonempty & ((1u << sub) - 1u));
+    // node allocation: one atomic per warp (up to 4 nodes being split), not one per node - millions of same-address
+    // atomics per generation serialise in L2
+    const int n0 = __shfl_sync(0xffffffffu, nchild, 0), n1 = __shfl_sync(0xffffffffu, nchild, 8), n2 = __shfl_sync(0xffffffffu, nchild, 16),
+              n3 = __shfl_sync(0xffffffffu, nchild, 24);
     int base = 0;
-    if (sub == 0) base = atomicAdd(&c->nnodes, nchild);
-    base = __shfl_sync(gmask, base, gshift);
+    if (lane == 0 && n0 + n1 + n2 + n3 > 0) base = atomicAdd(&c->nnodes, n0 + n1 + n2 + n3);
+    base = __shfl_sync(0xffffffffu, base, 0) + (gshift >= 8 ? n0 : 0) + (gshift >= 16 ? n1 : 0) + (gshift >= 24 ? n2 : 0);
     if (cc > 0) {
       const int child = base + slot;
       range[child] = make_int2(start, next);
@@ -301,18 +336,20 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
     // Walk groups. A cell with more than `super` bodies hands its small children (<= super bodies each) to the walk:
     // runs of consecutive small children (adjacent octants, contiguous bodies) are cut into equal chunks of <= group_size
     // bodies, so the walk's lanes are well filled while every chunk stays inside this cell.
-    if (cnt > super) {
+    const bool grouping = split && cnt > super;
+    if (__any_sync(0xffffffffu, grouping)) {
       int run_begin = 0, run_end = 0;
       for (int k = 0; k < 8; k++) {
-        const int ck = __shfl_sync(gmask, cc, gshift + k), sk = __shfl_sync(gmask, start, gshift + k);
-        if (sub != 0 || ck == 0) continue;
+        const int ck = __shfl_sync(0xffffffffu, cc, gshift + k), sk = __shfl_sync(0xffffffffu, start, gshift + k);
+        if (!grouping || sub != 0 || ck == 0) continue;
         if (ck <= super) { if (run_end == run_begin) run_begin = sk; run_end = sk + ck; }
         else { emit_groups(run_begin, run_end, group_size, groups, c); run_begin = run_end = 0; }
       }
-      if (sub == 0) emit_groups(run_begin, run_end, group_size, groups, c);
+      if (grouping && sub == 0) emit_groups(run_begin, run_end, group_size, groups, c);
     }
-    if (sub == 0) meta[node] = make_int4(base, nchild, level, m.w);
+    if (split && sub == 0) meta[node] = make_int4(base, nchild, level, m.w);
   }
+  (void)gmask;
   return maxlvl;
 }
 
@@ -414,7 +451,7 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
                      const float4* __restrict__ tgt, const int2* __restrict__ groups, Counters* __restrict__ c,
                      const float4* __restrict__ root, const float theta2, const float eps2, const float G, const int t0,
                      const int t1, const int accumulate, int* __restrict__ stacks, float4* __restrict__ acc,
-                     int* __restrict__ group_cost) {
+                     int* __restrict__ group_cost, uint32_t* __restrict__ bin_cost, const int n_targets) {
   // posm / node_* = the SOURCE tree; tgt / groups / c = the targets and their walk groups (the same tree, or - for
   // the locally-essential points received from other ranks - the local tree whose bodies are being accelerated)
   __shared__ __align__(16) float ring_all[kWalkWarps][4 * kListCap];
@@ -591,6 +628,9 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
     }
     inter += entries * (unsigned long long)ntarget;
     if (group_cost && lane == 0) group_cost[g] = (accumulate ? group_cost[g] : 0) + (int)min(entries, 0x3fffffffull);
+    // work record for the domain split: interactions of this group, binned by its position in the sorted order
+    if (bin_cost && lane == 0)
+      atomicAdd(bin_cost + min((int)((long long)r.x * kCostBins / max(n_targets, 1)), kCostBins - 1), (uint32_t)min(entries * (unsigned long long)ntarget, 0xffffffffull));
 #pragma unroll
     for (int k = 0; k < B; k++) {
       const int i = r.x + lane + 32 * k;
@@ -700,7 +740,7 @@ int launch_walk(Impl* m, Impl* g, const BHParams& p, const float4* posm, const f
   int per_sm = 0;
   NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<B, EPS0>, kWalkThreads, 0));
   if (p.leave_sm_slot) per_sm -= 1;   // room for a concurrent stream's kernels (LET exchange overlapped with this walk)
-  const int grid = kNumSMsB200 * std::max(1, std::min(per_sm, 8));
+  const int grid = sm_count() * std::max(1, std::min(per_sm, 8));
   const int64_t need = (int64_t)grid * kWalkWarps * kStackCap;
   if (need > m->cap_stacks) {
     NB_CUDA(cudaStreamSynchronize(s));
@@ -710,7 +750,7 @@ int launch_walk(Impl* m, Impl* g, const BHParams& p, const float4* posm, const f
   NB_CUDA(cudaMemsetAsync(&g->counters->next_group, 0, sizeof(int), s));
   bh_walk_group_kernel<B, EPS0><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, tgt, g->groups, g->counters, m->root,
                                                               p.theta * p.theta, p.eps2, p.G, t0, t1, accumulate ? 1 : 0,
-                                                              m->stacks, acc, g->group_cost);
+                                                              m->stacks, acc, g->group_cost, g->bin_cost, g->n);
   return 0;
 }
 
@@ -731,11 +771,11 @@ void bh_free(BHState& st) {
   if (!st.impl) return;
   Impl* m = static_cast<Impl*>(st.impl);
   for (int k = 0; k < 2; k++) { cudaFree(m->sort.keys[k]); cudaFree(m->sort.idx[k]); }
-  cudaFree(m->sort.hist); cudaFree(m->sort.tile_sums);
+  cudaFree(m->sort.work);
   cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->groups); cudaFree(m->group_cost);
   cudaFree(m->counters); cudaFree(m->root); cudaFree(m->stacks); cudaFree(m->boxes);
   cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_boxes); cudaFree(m->cut);
-  cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->let_cnt); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);
+  cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->bin_cost); cudaFree(m->ret); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);
   delete m;
   st.impl = nullptr;
 }
@@ -745,24 +785,30 @@ void bh_iota(int32_t* ids, int n, int first, cudaStream_t s) {
 }
 
 int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
-             float4* posm, float4* vel, int32_t* ids, int n, const uint32_t* box, cudaStream_t s, double* launches) {
+             float4* posm, float4* vel, int32_t* ids, int n, const uint32_t* box, cudaStream_t s, double* launches, const BodySegs* segs_in) {
   if (n <= 0) { set_error("Barnes-Hut: no bodies"); return -1; }
   if (n > (1 << 28)) { set_error("Barnes-Hut: at most 2^28 bodies per GPU"); return -1; }
   Impl* m = impl_of(st);
   NB_TRY(ensure(m, n, s));
   m->n = n;
   const unsigned nb = (unsigned)ceil_div(n, 256);
-  root_cube_kernel<<<1, 1, 0, s>>>(box, p.reference_root ? 1 : 0, m->root);
-  morton_kernel<<<nb, 256, 0, s>>>(posm_in, n, m->root, m->sort.keys[0]);
-  *launches += 2;
+  const BodySegs segs = segs_in ? *segs_in : BodySegs{0, n, 0};
+  if (!p.keep_root) {
+    root_cube_kernel<<<1, 1, 0, s>>>(box, p.reference_root ? 1 : (p.sticky_root ? 2 : 0), m->root);
+    *launches += 1;
+  }
   // Sort only as many levels as the tree needs: the last known depth + 4 (a cell at the last sorted level is a leaf
   // whatever it holds, so a too-small hint costs accuracy nothing, only walk efficiency, and corrects itself through
   // the depth statistic). The parity configurations (one-body leaves / per-body walk) always sort all 63 bits.
   int levels = kMaxLevel;
   if (p.leaf_size > 1 && p.mac == kMacGroup && p.depth_hint > 0) levels = std::min(kMaxLevel, std::max(10, p.depth_hint + 4));
-  m->sorted = radix_sort_pairs(m->sort, n, 3 * kMaxLevel, s, launches, 3 * (kMaxLevel - levels));
-  st.sort_passes_host = (3 * kMaxLevel + 7) / 8 - std::min(3 * (kMaxLevel - levels) / 8, (3 * kMaxLevel + 7) / 8 - 1);
-  gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[m->sorted], n, posm_in, vel_in, ids_in, posm, vel, ids);
+  const RadixPlan plan = radix_sort_begin(m->sort, n, 3 * kMaxLevel, s, 3 * (kMaxLevel - levels));
+  const unsigned nbk = (unsigned)std::min<int64_t>(nb, (int64_t)sm_count() * 16);   // grid-stride: few histogram flushes per CTA
+  morton_kernel<<<nbk, 256, 0, s>>>(posm_in, n, m->root, m->sort.keys[0], plan.ghist0, plan.shift0, segs);
+  *launches += 1;
+  m->sorted = radix_sort_run(m->sort, plan, n, s, launches);
+  st.sort_passes_host = plan.passes - plan.p0;
+  gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[m->sorted], n, segs, posm_in, vel_in, ids_in, posm, vel, ids);
   const uint64_t* keys = m->sort.keys[m->sorted];
   if (p.group_size != 32 && p.group_size != 64 && p.group_size != 128) { set_error("Barnes-Hut: group_size must be 32, 64 or 128"); return -1; }
   m->built_group_size = p.group_size;
@@ -781,7 +827,7 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
     }
     NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(sm_count() * (p.leave_sm_slot ? 1 : split_ctas)), dim3(256), args, 0, s));
   }
-  monopole_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
+  monopole_kernel<<<sm_count() * 8, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
   *launches += 2;
   NB_CUDA(cudaGetLastError());
   return 0;
@@ -851,7 +897,7 @@ int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t
   }
   int* d_count = reinterpret_cast<int*>(m->boxes + want * 7);
   NB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
-  leaf_boxes_kernel<<<kNumSMsB200 * 4, 256, 0, s>>>(m->sort.keys[m->sorted], m->node_meta, m->counters, m->root, m->boxes,
+  leaf_boxes_kernel<<<sm_count() * 4, 256, 0, s>>>(m->sort.keys[m->sorted], m->node_meta, m->counters, m->root, m->boxes,
                                                      (int)want, d_count);
   NB_CUDA(cudaGetLastError());
   int count = 0;
@@ -867,68 +913,102 @@ int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t
 // =====================================================================================================================
 // K9 - multi-GPU Barnes-Hut: Morton domain split, body migration and locally-essential-tree (LET) exchange.
 //
-// Every rank owns a contiguous range of the GLOBAL Morton order (keys are taken in one root cube shared by all ranks).
-// Per step:  (1) keys of the local bodies, regular key samples -> all-gather -> W-1 splitters (equal-WORK quantiles: a
-//                rank's samples are weighted by its body count and the time its walks took last step);
-//            (2) bodies are bucketed by destination rank (one 8-bit radix pass) and exchanged (all-to-all-v);
-//            (3) the local tree is built over the bodies now owned;
-//            (4) each rank publishes the bounding boxes of kLetBoxes cells of its local tree (a cut below the root); for every peer the local tree is
-//                descended generation by generation with the reference's acceptance rule taken against the NEAREST of
-//                that peer's boxes (so it holds for every body of the peer): accepted cells are exported as point
-//                masses, opened leaves as bodies;
-//            (5) export lists are exchanged (all-to-all-v); the received points get their own tree;
-//            (6) every local walk group is walked through the local tree and then through the LET tree.
+// Every rank owns a contiguous range of the GLOBAL Morton order: keys are taken in one root cube shared by all ranks
+// (sticky: it only changes when bodies leave it or it becomes far too large, so keys and splitters stay comparable from
+// step to step). splitters[r] = first key of rank r's domain.
+//   when the bodies are set (bh_let_redistribute, eager): keys -> regular samples -> all-gather -> splitters (kept ones
+//       are reused when the caller sets the bodies again) -> bodies bucketed by destination and exchanged.
+//   per step, ONE host synchronisation:
+//     (1) local sort + tree over the bodies held now (bh_build);
+//     (2) bh_let_plan: where the sorted bodies would go under the current splitters (a prefix leaves to lower ranks, a
+//         suffix to higher ranks: lower bounds of the splitters in the sorted keys); the rank's domain boxes (a cut of
+//         its tree) are all-gathered; the local tree is descended for all peers at once with the reference's acceptance
+//         rule taken against the NEAREST box of each peer (so it holds for every body of the peer): accepted cells are
+//         exported as point masses, opened leaves as bodies; export counts and migration counts travel in one all-gather,
+//         which the host reads (the one synchronisation);
+//     (3) bh_let_import: export lists exchanged (all-to-all-v), the received points get their own tree; meanwhile the
+//         local walk runs on the main stream; then the walk over the received points;
+//     (4) bh_let_finish, after the kick-drift: new splitters = equal-WORK quantiles (the walks add each group's
+//         interaction count into 1024 bins along the sorted bodies; every rank contributes 256 equal-work samples),
+//         damped by one half; then the bodies that left the rank's key range are sent to their new owners and the
+//         received ones appended - LAZILY: they were still this rank's targets in this step. Ownership only affects
+//         balance, never results: a rank's boxes always cover the bodies it actually holds.
 // The reference has no counterpart (it is single threaded); forces equal the single-GPU walk up to the (stricter)
 // acceptance of remote cells and summation order.
 // =====================================================================================================================
 namespace {
 
-// A rank's message to the splitter selection: kLetSamples keys at regular positions of its (nearly Morton-sorted) bodies
-// + its body count + the device time its walks took last step (0 = unknown).
+// A rank's message to the splitter selection: kLetSamples keys + its weight (float bits: work or body count) + its body count.
 constexpr int kLetMsg = kLetSamples + 2;
 
-__global__ void let_sample_kernel(const uint64_t* __restrict__ keys, const int n, const float walk_ms, uint64_t* __restrict__ out) {
+// Regular positions of the (unsorted or sorted) local keys, weight = body count.
+__global__ void let_sample_regular_kernel(const uint64_t* __restrict__ keys, const int n, uint64_t* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < kLetSamples) {
     const int j = min((int)(((long long)i * n + n / 2) / kLetSamples), n - 1);
     out[i] = n > 0 ? keys[j] : ~0ull;
   } else if (i == kLetSamples) {
-    out[i] = (uint64_t)n;
+    out[i] = (uint64_t)__float_as_uint((float)n);
   } else if (i == kLetSamples + 1) {
-    out[i] = (uint64_t)__float_as_uint(walk_ms);
+    out[i] = (uint64_t)n;
   }
 }
 
-// One CTA: sort the gathered samples by key (bitonic, shared memory) and cut them into `world` pieces of equal WEIGHT.
-// A sample of rank q stands for 1/kLetSamples of that rank's cost = (1 - time_weight) x its share of the bodies +
-// time_weight x its share of last step's walk time. time_weight = 0 (default) gives equal counts; on 8 GPUs / 16M
-// two-galaxy bodies 0.7 moved the boundaries too much per step (more migration than the walks gained, 94 vs 109 steps/s).
+// Equal-WORK positions of the sorted local keys: bin_cost[b] = interactions evaluated for the bodies of bin b (equal-count
+// bins along the sorted order). One CTA of kCostBins threads. Falls back to regular positions when nothing was counted.
+__global__ void __launch_bounds__(kCostBins)
+let_sample_cost_kernel(const uint64_t* __restrict__ keys, const int n, const uint32_t* __restrict__ bin_cost, uint64_t* __restrict__ out) {
+  __shared__ float pre[kCostBins + 1];
+  __shared__ float wsum[kCostBins / 32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  float v = (float)bin_cost[t] + 1.0f;        // + 1: empty bins keep a little weight, positions stay strictly increasing
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    float s = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float x = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += x; }
+    wsum[lane] = s;
+  }
+  __syncthreads();
+  pre[t + 1] = inc + (w ? wsum[w - 1] : 0.f);
+  if (t == 0) pre[0] = 0.f;
+  __syncthreads();
+  const float total = pre[kCostBins];
+  if (t < kLetSamples) {
+    uint64_t key = ~0ull;
+    if (n > 0) {
+      const float target = total * ((float)t + 0.5f) / (float)kLetSamples;
+      int lo = 0, hi = kCostBins;                     // first bin whose inclusive prefix reaches the target
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (pre[mid + 1] < target) lo = mid + 1; else hi = mid; }
+      const int b = min(lo, kCostBins - 1);
+      const float frac = fminf(fmaxf((target - pre[b]) / fmaxf(pre[b + 1] - pre[b], 1e-20f), 0.f), 1.f);
+      const long long pos = (long long)(((double)b + (double)frac) * (double)n / (double)kCostBins);
+      key = keys[min(max(pos, 0ll), (long long)n - 1)];
+    }
+    out[t] = key;
+  } else if (t == kLetSamples) {
+    out[t] = (uint64_t)__float_as_uint(n > 0 ? total : 0.f);
+  } else if (t == kLetSamples + 1) {
+    out[t] = (uint64_t)n;
+  }
+}
+
+// One CTA: sort the gathered samples by key (bitonic, shared memory) and cut them into `world` pieces of equal WEIGHT: a
+// sample of rank q stands for 1 / kLetSamples of that rank's weight. splitters[0] = 0, splitters[world] = ~0; the inner
+// ones move a fraction `alpha` of the way from their previous value to the new quantile (alpha = 1: jump).
 __global__ void __launch_bounds__(1024)
-let_splitters_kernel(const uint64_t* __restrict__ msgs, const int world, const float time_weight,
-                     uint64_t* __restrict__ splitters) {
+let_splitters_kernel(const uint64_t* __restrict__ msgs, const int world, const float alpha, uint64_t* __restrict__ splitters) {
   extern __shared__ uint64_t sk[];                 // [pow2] keys, then [pow2] floats (weights -> inclusive prefix)
   const int total = world * kLetSamples;
   int pow2 = 1;
   while (pow2 < total) pow2 <<= 1;
   float* sw = reinterpret_cast<float*>(sk + pow2);
   __shared__ float wq[kMaxWorld];
-  if (threadIdx.x == 0) {
-    double sum_n = 0, sum_t = 0;
-    bool timed = true;
-    for (int q = 0; q < world; q++) {
-      const double nq = (double)msgs[(size_t)q * kLetMsg + kLetSamples];
-      const float tq = __uint_as_float((uint32_t)msgs[(size_t)q * kLetMsg + kLetSamples + 1]);
-      sum_n += nq; sum_t += tq;
-      if (nq > 0 && !(tq > 0.f)) timed = false;      // some rank has no timing yet: fall back to counts
-    }
-    for (int q = 0; q < world; q++) {
-      const double nq = (double)msgs[(size_t)q * kLetMsg + kLetSamples];
-      const float tq = __uint_as_float((uint32_t)msgs[(size_t)q * kLetMsg + kLetSamples + 1]);
-      double w = sum_n > 0 ? nq / sum_n : 1.0 / world;
-      if (timed && sum_t > 0 && time_weight > 0.f) w = (1.0 - time_weight) * w + (double)time_weight * (double)tq / sum_t;
-      wq[q] = (float)(w / kLetSamples);
-    }
-  }
+  if (threadIdx.x < world) wq[threadIdx.x] = __uint_as_float((uint32_t)msgs[(size_t)threadIdx.x * kLetMsg + kLetSamples]) / (float)kLetSamples;
   __syncthreads();
   for (int i = threadIdx.x; i < pow2; i += blockDim.x) {
     const int q = i / kLetSamples;
@@ -963,16 +1043,22 @@ let_splitters_kernel(const uint64_t* __restrict__ msgs, const int world, const f
     const float hi = sw[i], lo = i ? sw[i - 1] : 0.f;
     for (int r = 1; r < world; r++) {
       const float target = all * (float)r / (float)world;
-      if (lo < target && target <= hi) splitters[r - 1] = sk[i];
+      if (lo < target && target <= hi) {
+        const uint64_t tgt = sk[i], old = splitters[r];
+        uint64_t nw = tgt;
+        if (alpha < 1.f) nw = tgt >= old ? old + (uint64_t)((double)(tgt - old) * (double)alpha) : old - (uint64_t)((double)(old - tgt) * (double)alpha);
+        splitters[r] = nw;
+      }
     }
   }
+  if (threadIdx.x == 0) { splitters[0] = 0ull; splitters[world] = ~0ull; }
 }
 
-// keys[i] <- destination rank of body i = number of splitters <= key (bodies with equal keys stay together).
+// keys[i] <- destination rank of body i = number of inner splitters <= key (bodies with equal keys stay together).
 __global__ void __launch_bounds__(256)
 let_dest_kernel(uint64_t* __restrict__ keys, const int n, const uint64_t* __restrict__ splitters, const int world) {
   __shared__ uint64_t sp[kMaxWorld];
-  if (threadIdx.x < world - 1) sp[threadIdx.x] = splitters[threadIdx.x];
+  if (threadIdx.x < world - 1) sp[threadIdx.x] = splitters[threadIdx.x + 1];
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -982,34 +1068,60 @@ let_dest_kernel(uint64_t* __restrict__ keys, const int n, const uint64_t* __rest
   keys[i] = (uint64_t)d;
 }
 
-// send_off[r] = first position in the destination-sorted array whose destination is >= r.
-__global__ void let_offsets_kernel(const uint64_t* __restrict__ dest_sorted, const int n, const int world, int* __restrict__ send_off) {
+// send_off[r] = first position of the sorted values whose value is >= bound_r (bound_r = r for destination-sorted bodies,
+// splitters[r] for key-sorted bodies); send_off[world] = n.
+__global__ void let_offsets_kernel(const uint64_t* __restrict__ sorted, const int n, const int world, const uint64_t* __restrict__ splitters,
+                                   int* __restrict__ send_off) {
   const int r = threadIdx.x;
   if (r > world) return;
+  const uint64_t bound = splitters ? splitters[r] : (uint64_t)r;
   int lo = 0, hi = n;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (dest_sorted[mid] < (uint64_t)r) lo = mid + 1; else hi = mid; }
+  if (r == world) lo = n;
+  else while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted[mid] < bound) lo = mid + 1; else hi = mid; }
   send_off[r] = lo;
 }
 
 // A rank describes its domain to its peers by the bounding boxes of a CUT of its local tree: starting from the root,
 // the cell with the most bodies is replaced by its children until kLetBoxes cells are reached. Tree cells are spatially
-// compact (a Morton range is not: it can jump across the whole cube), so the boxes hug the bodies.
-__global__ void let_cut_kernel(const int4* __restrict__ meta, const int2* __restrict__ range, const int n, int2* __restrict__ cut) {
-  int node[kLetBoxes], cnt = 0;
-  if (n > 0) node[cnt++] = 0;
+// compact (a Morton range is not: it can jump across the whole cube), so the boxes hug the bodies. One warp: the
+// candidates live one per lane (two per lane for the second half), the arg-max is a warp reduction.
+__global__ void __launch_bounds__(32)
+let_cut_kernel(const int4* __restrict__ meta, const int2* __restrict__ range, const int n, int2* __restrict__ cut) {
+  __shared__ int node[kLetBoxes];
+  __shared__ int bodies[kLetBoxes];   // bodies of an internal candidate, 0 for leaves (never split)
+  const int lane = threadIdx.x;
+  int cnt = 0;
+  if (n > 0) {
+    if (lane == 0) { node[0] = 0; const int4 m = meta[0]; bodies[0] = (m.z & kLeafFlag) ? 0 : n; }
+    cnt = 1;
+  }
+  __syncwarp();
   while (cnt > 0 && cnt < kLetBoxes) {
-    int best = -1, best_bodies = 1;
-    for (int k = 0; k < cnt; k++) {
-      const int4 m = meta[node[k]];
-      const int2 r = range[node[k]];
-      if (!(m.z & kLeafFlag) && r.y - r.x > best_bodies && cnt - 1 + m.y <= kLetBoxes) { best = k; best_bodies = r.y - r.x; }
+    // candidate with the most bodies whose children still fit
+    int best = -1, bb = 1;
+    for (int k = lane; k < cnt; k += 32) {
+      const int b = bodies[k];
+      if (b > bb && cnt - 1 + meta[node[k]].y <= kLetBoxes) { best = k; bb = b; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ob = __shfl_xor_sync(0xffffffffu, bb, o), ok = __shfl_xor_sync(0xffffffffu, best, o);
+      if (ob > bb || (ob == bb && ok >= 0 && (best < 0 || ok < best))) { bb = ob; best = ok; }
     }
     if (best < 0) break;
     const int4 m = meta[node[best]];
-    node[best] = m.x;
-    for (int k = 1; k < m.y; k++) node[cnt++] = m.x + k;
+    __syncwarp();
+    if (lane < m.y) {
+      const int child = m.x + lane, slot = lane == 0 ? best : cnt + lane - 1;
+      const int4 cm = meta[child];
+      const int2 cr = range[child];
+      node[slot] = child;
+      bodies[slot] = (cm.z & kLeafFlag) ? 0 : cr.y - cr.x;
+    }
+    cnt += m.y - 1;
+    __syncwarp();
   }
-  for (int k = 0; k < kLetBoxes; k++) cut[k] = k < cnt ? range[node[k]] : make_int2(0, 0);
+  for (int k = lane; k < kLetBoxes; k += 32) cut[k] = k < cnt ? range[node[k]] : make_int2(0, 0);
 }
 
 // Box b = bounding box of the bodies of cut cell b; unused entries get an inverted box that is infinitely far from
@@ -1041,13 +1153,23 @@ let_boxes_kernel(const float4* __restrict__ posm, const int2* __restrict__ cut, 
 }
 
 // The export descent, all peers at once, all generations in one cooperative launch. visit[node] = bit mask of the
-// peers that reached this node (written by the parent one generation earlier).
+// peers that reached this node (written by the parent one generation earlier). A peer's boxes are tested hull first:
+// a cell accepted against the hull of all its boxes is accepted against each of them.
 __global__ void __launch_bounds__(256)
 let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com,
                   const int4* __restrict__ node_meta, const Counters* __restrict__ c, const float4* __restrict__ root,
                   const float* __restrict__ peer_boxes, const int world, const int rank, const float theta2,
                   uint32_t* __restrict__ visit, float4* __restrict__ let_out, int* __restrict__ let_cnt, const int cap_let) {
   cg::grid_group grid = cg::this_grid();
+  __shared__ float hull[kMaxWorld][6];
+  if (threadIdx.x < world) {
+    const float* bx = peer_boxes + (size_t)threadIdx.x * kLetBoxes * 6;
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int b = 0; b < kLetBoxes; b++)
+      for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], bx[b * 6 + k]); mx[k] = fmaxf(mx[k], bx[b * 6 + 3 + k]); }
+    for (int k = 0; k < 3; k++) { hull[threadIdx.x][k] = mn[k]; hull[threadIdx.x][3 + k] = mx[k]; }
+  }
+  __syncthreads();
   const float root_half = root[0].w;
   for (int gen = 0; gen <= kMaxLevel; gen++) {
   const int gb = c->gen_off[gen], ge = c->gen_off[gen + 1];
@@ -1060,17 +1182,28 @@ let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ no
     if (mask) {
       const float4 cm = node_com[node];
       const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);
+      const float need = size * size / fmaxf(theta2, 1e-30f);      // accepted  <=>  dmin^2 > need
+      const bool single = leaf && m.y == 1;
       for (int p = 0; p < world; p++) {
         if (!(mask >> p & 1u)) continue;
-        const float* bx = peer_boxes + (size_t)p * kLetBoxes * 6;
-        float dmin2 = 3.0e38f;
-        for (int b = 0; b < kLetBoxes; b++) {
-          const float dx = fmaxf(fmaxf(bx[b * 6] - cm.x, cm.x - bx[b * 6 + 3]), 0.f);
-          const float dy = fmaxf(fmaxf(bx[b * 6 + 1] - cm.y, cm.y - bx[b * 6 + 4]), 0.f);
-          const float dz = fmaxf(fmaxf(bx[b * 6 + 2] - cm.z, cm.z - bx[b * 6 + 5]), 0.f);
-          dmin2 = fminf(dmin2, dx * dx + dy * dy + dz * dz);
+        bool accept = single;
+        if (!accept) {
+          const float hx = fmaxf(fmaxf(hull[p][0] - cm.x, cm.x - hull[p][3]), 0.f), hy = fmaxf(fmaxf(hull[p][1] - cm.y, cm.y - hull[p][4]), 0.f),
+                      hz = fmaxf(fmaxf(hull[p][2] - cm.z, cm.z - hull[p][5]), 0.f);
+          accept = theta2 > 0.f && hx * hx + hy * hy + hz * hz > need;
+          if (!accept && theta2 > 0.f) {
+            const float* bx = peer_boxes + (size_t)p * kLetBoxes * 6;
+            float dmin2 = 3.0e38f;
+            for (int b = 0; b < kLetBoxes; b++) {
+              const float dx = fmaxf(fmaxf(bx[b * 6] - cm.x, cm.x - bx[b * 6 + 3]), 0.f);
+              const float dy = fmaxf(fmaxf(bx[b * 6 + 1] - cm.y, cm.y - bx[b * 6 + 4]), 0.f);
+              const float dz = fmaxf(fmaxf(bx[b * 6 + 2] - cm.z, cm.z - bx[b * 6 + 5]), 0.f);
+              dmin2 = fminf(dmin2, dx * dx + dy * dy + dz * dz);
+            }
+            accept = dmin2 > need;
+          }
         }
-        if (size * size < theta2 * dmin2 || (leaf && m.y == 1)) {
+        if (accept) {
           const int slot = atomicAdd(let_cnt + p, 1);
           if (slot < cap_let) let_out[(size_t)p * cap_let + slot] = cm;
         } else if (leaf) {
@@ -1087,17 +1220,45 @@ let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ no
   }
 }
 
+// Records of the bodies in owner order -> one staging array; out[i] = rec[order[i]] (rec_words floats each) and the id.
+__global__ void __launch_bounds__(256)
+let_pack_records_kernel(const uint32_t* __restrict__ order, const int n, const float* __restrict__ rec, const int rec_words,
+                        const int32_t* __restrict__ ids, float* __restrict__ out, int32_t* __restrict__ ids_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t j = order[i];
+  for (int k = 0; k < rec_words; k++) out[(size_t)i * rec_words + k] = rec[(size_t)j * rec_words + k];
+  ids_out[i] = ids[j];
+}
+__global__ void __launch_bounds__(256)
+let_owner_kernel(const int32_t* __restrict__ ids, const int n, const int64_t n_per, const int world, uint64_t* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = (uint64_t)min((int64_t)world - 1, (int64_t)ids[i] / n_per);
+}
+__global__ void __launch_bounds__(256)
+let_unpack_records_kernel(const float* __restrict__ rec, const int32_t* __restrict__ ids, const int n, const int rec_words,
+                          const int64_t first, const int n_slice, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t row = (int64_t)ids[i] - first;
+  if (row < 0 || row >= n_slice) return;
+  for (int k = 0; k < rec_words; k++) out[(size_t)row * rec_words + k] = rec[(size_t)i * rec_words + k];
+}
+
 int let_ensure(Impl* m, int world, int64_t cap_local, cudaStream_t s) {
   if (m->let_world != world) {
     NB_CUDA(cudaStreamSynchronize(s));
     NB_TRY(realloc_dev(&m->samples, (size_t)(world + 1) * kLetMsg));
-    NB_TRY(realloc_dev(&m->splitters, (size_t)world));
-    NB_TRY(realloc_dev(&m->send_off, (size_t)world + 1));
-    NB_TRY(realloc_dev(&m->all_off, (size_t)world * (world + 1)));
+    NB_TRY(realloc_dev(&m->splitters, (size_t)world + 1));
+    NB_TRY(realloc_dev(&m->send_off, (size_t)2 * world + 2));
+    NB_TRY(realloc_dev(&m->all_off, (size_t)world * (2 * world + 2)));
     NB_TRY(realloc_dev(&m->peer_boxes, (size_t)world * kLetBoxes * 6));
-    NB_TRY(realloc_dev(&m->let_cnt, (size_t)world));
     NB_TRY(realloc_dev(&m->cut, (size_t)kLetBoxes));
+    NB_TRY(realloc_dev(&m->bin_cost, (size_t)kCostBins));
+    NB_CUDA(cudaMemsetAsync(m->bin_cost, 0, kCostBins * sizeof(uint32_t), s));
+    m->let_cnt = m->send_off + world + 1;      // the per-step count message: [world + 1] send_off | [world] export counts
     m->let_world = world;
+    m->splitters_valid = false;
   }
   if (cap_local > m->cap_let) {
     NB_CUDA(cudaStreamSynchronize(s));
@@ -1107,37 +1268,51 @@ int let_ensure(Impl* m, int world, int64_t cap_local, cudaStream_t s) {
   return 0;
 }
 
+int launch_splitters(Impl* m, int world, float alpha, cudaStream_t s) {
+  int pow2 = 1;
+  while (pow2 < world * kLetSamples) pow2 <<= 1;
+  NB_CUDA(cudaFuncSetAttribute(let_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12));   // world 9..16: 48 KB + static
+  let_splitters_kernel<<<1, 1024, (size_t)pow2 * 12, s>>>(m->samples, world, alpha, m->splitters);
+  NB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
-// Phases (1)-(2): on return the first *n_local entries of posm_a / vel_a / ids_a hold the bodies this rank owns now
-// (`world` runs received from the peers, not yet sorted). posm_b / vel_b / ids_b are scratch (send staging).
-int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
-                   float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, float walk_ms, int* n_local,
-                   cudaStream_t s, double* launches) {
+void bh_let_forget_domains(BHState& st) { if (st.impl) static_cast<Impl*>(st.impl)->splitters_valid = false; }
+
+// When the bodies are set: on return the first *n_local entries of posm_a / vel_a / ids_a hold the bodies of this rank's
+// domain (`world` runs received from the peers, not yet sorted). posm_b / vel_b / ids_b are scratch (send staging).
+// Splitters from an earlier run of this handle are reused (the caller uploads the same system again: the domains are
+// already balanced for it); otherwise they are equal-count quantiles of regular key samples.
+int bh_let_redistribute(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
+                        float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local,
+                        cudaStream_t s, double* launches) {
   Impl* m = impl_of(st);
   const int world = comm->world(), rank = comm->rank();
   if (world > kMaxWorld) { set_error("Barnes-Hut LET: at most 16 ranks"); return -1; }
   NB_TRY(ensure(m, (int)std::max<int64_t>(cap, 1), s));
   NB_TRY(let_ensure(m, world, cap, s));
   const unsigned nb = (unsigned)ceil_div(std::max(n, 1), 256);
-  root_cube_kernel<<<1, 1, 0, s>>>(box_global, p.reference_root ? 1 : 0, m->root);
-  if (n > 0) morton_kernel<<<nb, 256, 0, s>>>(posm_a, n, m->root, m->sort.keys[0]);
-  let_sample_kernel<<<1, 288, 0, s>>>(m->sort.keys[0], n, walk_ms, m->samples + (size_t)world * kLetMsg);
-  NB_TRY(comm->all_gather_bytes(m->samples + (size_t)world * kLetMsg, m->samples, (size_t)kLetMsg * 8, s));
-  int pow2 = 1;
-  while (pow2 < world * kLetSamples) pow2 <<= 1;
-  NB_CUDA(cudaFuncSetAttribute(let_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12));   // world 9..16: 48 KB + static
-  let_splitters_kernel<<<1, 1024, (size_t)pow2 * 12, s>>>(m->samples, world, p.let_time_weight, m->splitters);
-  NB_CUDA(cudaGetLastError());
-  *launches += 4;
+  root_cube_kernel<<<1, 1, 0, s>>>(box_global, p.reference_root ? 1 : (p.sticky_root ? 2 : 0), m->root);
+  if (n > 0) morton_kernel<<<nb, 256, 0, s>>>(posm_a, n, m->root, m->sort.keys[0], nullptr, 0);
+  *launches += 2;
+  if (!m->splitters_valid) {
+    let_sample_regular_kernel<<<1, 288, 0, s>>>(m->sort.keys[0], n, m->samples + (size_t)world * kLetMsg);
+    NB_TRY(comm->all_gather_bytes(m->samples + (size_t)world * kLetMsg, m->samples, (size_t)kLetMsg * 8, s));
+    NB_TRY(launch_splitters(m, world, 1.f, s));
+    *launches += 2;
+    m->splitters_valid = true;
+  }
   int sorted = 0;
   if (n > 0) {
     let_dest_kernel<<<nb, 256, 0, s>>>(m->sort.keys[0], n, m->splitters, world);
     sorted = radix_sort_pairs(m->sort, n, 8, s, launches);     // one pass: stable bucket by destination rank
-    gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[sorted], n, posm_a, vel_a, ids_a, posm_b, vel_b, ids_b);
+    gather_bodies_kernel<<<nb, 256, 0, s>>>(m->sort.idx[sorted], n, BodySegs{0, n, 0}, posm_a, vel_a, ids_a, posm_b, vel_b, ids_b);
     *launches += 2;
   }
-  let_offsets_kernel<<<1, 32, 0, s>>>(m->sort.keys[sorted], n, world, m->send_off);
+  let_offsets_kernel<<<1, 32, 0, s>>>(m->sort.keys[sorted], n, world, nullptr, m->send_off);
+  *launches += 1;
   NB_TRY(comm->all_gather_bytes(m->send_off, m->all_off, (size_t)(world + 1) * 4, s));
   std::vector<int> off((size_t)world * (world + 1));
   NB_CUDA(cudaMemcpyAsync(off.data(), m->all_off, off.size() * 4, cudaMemcpyDeviceToHost, s));
@@ -1159,6 +1334,7 @@ int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, f
     if (total_d > cap) {
       set_error("Barnes-Hut LET: the domain of rank " + std::to_string(d) + " outgrew the body buffers (" + std::to_string(total_d) + " > " +
                 std::to_string(cap) + ")");
+      m->splitters_valid = false;
       return -5;
     }
   }
@@ -1176,25 +1352,27 @@ int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, f
   return 0;
 }
 
-// Phases (4)-(5): `local` holds the tree of the n sorted local bodies posm. Builds `let` over the points received from
-// the peers (n_let of them; 0 is possible).
-int bh_let_exchange(BHState& local, BHState& let, Comm* comm, const BHParams& p, const float4* posm, int n,
-                    const uint32_t* box_global, int* n_let, cudaStream_t s, double* launches) {
+// Step phase (2): `local` holds the tree of the n sorted local bodies posm. Fills plan (host) after the step's one
+// host synchronisation.
+int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* posm, int n, int64_t cap, LetPlan* plan, cudaStream_t s,
+                double* launches) {
   Impl* m = impl_of(local);
   const int world = comm->world(), rank = comm->rank();
-  NB_TRY(let_ensure(m, world, std::max<int64_t>(m->cap_n, 1024), s));
+  NB_TRY(let_ensure(m, world, std::max<int64_t>(cap, 1024), s));
   const int64_t need_nodes = std::max<int64_t>(m->cap_nodes, 16);
   if (need_nodes > m->cap_visit) {
     NB_CUDA(cudaStreamSynchronize(s));
     NB_TRY(realloc_dev(&m->visit, (size_t)need_nodes));
     m->cap_visit = need_nodes;
   }
+  // where the sorted bodies go under the current splitters
+  let_offsets_kernel<<<1, 32, 0, s>>>(m->sort.keys[m->sorted], n, world, m->splitters, m->send_off);
   float* my_boxes = m->peer_boxes + (size_t)rank * kLetBoxes * 6;
-  let_cut_kernel<<<1, 1, 0, s>>>(m->node_meta, m->node_range, n, m->cut);
+  let_cut_kernel<<<1, 32, 0, s>>>(m->node_meta, m->node_range, n, m->cut);
   let_boxes_kernel<<<kLetBoxes, 256, 0, s>>>(posm, m->cut, my_boxes);
+  *launches += 3;
   NB_TRY(comm->all_gather_bytes(my_boxes, m->peer_boxes, (size_t)kLetBoxes * 6 * 4, s));
   NB_CUDA(cudaMemsetAsync(m->let_cnt, 0, (size_t)world * 4, s));
-  *launches += 1;
   if (n > 0) {
     int w = world, r = rank, cap_let = (int)m->cap_let;
     float theta2 = p.theta * p.theta;
@@ -1203,36 +1381,183 @@ int bh_let_exchange(BHState& local, BHState& let, Comm* comm, const BHParams& p,
     NB_CUDA(cudaLaunchCooperativeKernel((void*)let_export_kernel, dim3(sm_count()), dim3(256), args, 0, s));
     *launches += 1;
   }
-  NB_TRY(comm->all_gather_bytes(m->let_cnt, m->all_off, (size_t)world * 4, s));
-  std::vector<int> cnt((size_t)world * world);
-  NB_CUDA(cudaMemcpyAsync(cnt.data(), m->all_off, cnt.size() * 4, cudaMemcpyDeviceToHost, s));
+  // one message per rank: [world + 1] migration offsets | [world] export counts; one all-gather, one host read
+  const int msg = 2 * world + 1;
+  NB_TRY(comm->all_gather_bytes(m->send_off, m->all_off, (size_t)msg * 4, s));
+  std::vector<int> all((size_t)world * msg);
+  NB_CUDA(cudaMemcpyAsync(all.data(), m->all_off, all.size() * 4, cudaMemcpyDeviceToHost, s));
   NB_CUDA(cudaStreamSynchronize(s));
+  plan->world = world; plan->rank = rank; plan->n = n;
+  // cap_let is the same on every rank (it derives from the body capacity), so an overflow anywhere fails everywhere
+  for (int q = 0; q < world; q++)
+    for (int d = 0; d < world; d++)
+      if (all[(size_t)q * msg + world + 1 + d] > m->cap_let) {
+        set_error("Barnes-Hut LET: export list overflow (" + std::to_string(all[(size_t)q * msg + world + 1 + d]) + " > " + std::to_string(m->cap_let) + ")");
+        return -5;
+      }
+  int64_t let_total = 0;
+  bool fits = true;
+  for (int q = 0; q < world; q++) {
+    const int* theirs = all.data() + (size_t)q * msg;
+    plan->send_off[q] = all[(size_t)rank * msg + q];
+    plan->mig_recv[q] = q == rank ? 0 : theirs[rank + 1] - theirs[rank];
+    plan->let_send[q] = all[(size_t)rank * msg + world + 1 + q];
+    plan->let_recv[q] = theirs[world + 1 + rank];
+    let_total += plan->let_recv[q];
+  }
+  plan->send_off[world] = all[(size_t)rank * msg + world];
+  // lazy migration is taken only when it fits on EVERY rank (all ranks evaluate the same numbers: same decision)
+  for (int d = 0; d < world; d++) {
+    int64_t incoming = 0;
+    for (int q = 0; q < world; q++) if (q != d) incoming += all[(size_t)q * msg + d + 1] - all[(size_t)q * msg + d];
+    const int64_t n_d = all[(size_t)d * msg + world];
+    if (n_d + incoming > cap) fits = false;
+  }
+  plan->migrate = fits;
+  plan->let_total = let_total;
+  return 0;
+}
+
+// Step phase (3): exchange the export lists; `let` gets the tree over the points received (n_let of them; 0 is possible).
+int bh_let_import(BHState& local, BHState& let, Comm* comm, const BHParams& p, const LetPlan& plan, const uint32_t* box_global, int* n_let,
+                  cudaStream_t s, double* launches) {
+  Impl* m = impl_of(local);
+  const int world = plan.world;
   size_t sb[kMaxWorld], so[kMaxWorld], rb[kMaxWorld], ro[kMaxWorld];
   int64_t total = 0;
-  // cap_let is the same on every rank (it derives from the body capacity), so an overflow anywhere fails everywhere
-  for (size_t k = 0; k < cnt.size(); k++)
-    if (cnt[k] > m->cap_let) { set_error("Barnes-Hut LET: export list overflow (" + std::to_string(cnt[k]) + " > " + std::to_string(m->cap_let) + ")"); return -5; }
   for (int q = 0; q < world; q++) {
-    const int mine = cnt[(size_t)rank * world + q], theirs = cnt[(size_t)q * world + rank];
-    sb[q] = (size_t)mine * 16; so[q] = (size_t)q * (size_t)m->cap_let * 16;
-    rb[q] = (size_t)theirs * 16; ro[q] = (size_t)total * 16;
-    total += theirs;
+    sb[q] = (size_t)plan.let_send[q] * 16; so[q] = (size_t)q * (size_t)m->cap_let * 16;
+    rb[q] = (size_t)plan.let_recv[q] * 16; ro[q] = (size_t)total * 16;
+    total += plan.let_recv[q];
   }
   if (total > m->cap_let_in) {
     const int64_t c = total + total / 4 + 4096;
+    NB_CUDA(cudaStreamSynchronize(s));
     NB_TRY(realloc_dev(&m->let_in, (size_t)c));
     NB_TRY(realloc_dev(&m->let_sorted, (size_t)c));
     m->cap_let_in = c;
   }
   NB_TRY(comm->all_to_all_v(m->let_out, sb, so, m->let_in, rb, ro, s));
   *n_let = (int)total;
-  if (total > 0)
-    NB_TRY(bh_build(let, p, m->let_in, nullptr, nullptr, m->let_sorted, nullptr, nullptr, (int)total, box_global, s, launches));
+  if (total > 0) {
+    BHParams q = p;
+    q.sticky_root = false;           // same cube as the local tree: copy it instead of deriving it again
+    Impl* l = impl_of(let);
+    NB_TRY(ensure(l, (int)total, s));
+    NB_CUDA(cudaMemcpyAsync(l->root, m->root, sizeof(float4), cudaMemcpyDeviceToDevice, s));
+    q.keep_root = true;
+    NB_TRY(bh_build(let, q, m->let_in, nullptr, nullptr, m->let_sorted, nullptr, nullptr, (int)total, box_global, s, launches));
+  }
   NB_CUDA(cudaGetLastError());
   return 0;
 }
 
 const float4* bh_let_sources(BHState& local) { return impl_of(local)->let_sorted; }
+
+// Step phase (4), after the kick-drift: new splitters from equal-work samples (damped), then the planned migration.
+// posm / vel / ids = the step's sorted arrays (capacity cap): the leaving prefix and suffix are sent, the arriving
+// bodies land behind the current ones; *next describes where the bodies of the next step sit.
+int bh_let_finish(BHState& local, Comm* comm, const BHParams& p, const LetPlan& plan, float4* posm, float4* vel, float4* acc, int32_t* ids,
+                  BodySegs* next, int* n_next, int* n_received, cudaStream_t s, double* launches) {
+  Impl* m = impl_of(local);
+  const int world = plan.world, rank = plan.rank, n = plan.n;
+  // (a) splitters for the next step
+  let_sample_cost_kernel<<<1, kCostBins, 0, s>>>(m->sort.keys[m->sorted], n, m->bin_cost, m->samples + (size_t)world * kLetMsg);
+  NB_TRY(comm->all_gather_bytes(m->samples + (size_t)world * kLetMsg, m->samples, (size_t)kLetMsg * 8, s));
+  NB_TRY(launch_splitters(m, world, p.let_damping, s));
+  NB_CUDA(cudaMemsetAsync(m->bin_cost, 0, kCostBins * sizeof(uint32_t), s));
+  *launches += 2;
+  // (b) migration as planned before the walks
+  *next = BodySegs{0, n, 0};
+  *n_next = n;
+  *n_received = 0;
+  if (!plan.migrate) return 0;
+  size_t sb[kMaxWorld], so[kMaxWorld], rb[kMaxWorld], ro[kMaxWorld];
+  int64_t incoming = 0;
+  for (int q = 0; q < world; q++) {
+    sb[q] = q == rank ? 0 : (size_t)(plan.send_off[q + 1] - plan.send_off[q]);
+    so[q] = (size_t)plan.send_off[q];
+    rb[q] = (size_t)plan.mig_recv[q];
+    ro[q] = (size_t)n + (size_t)incoming;
+    incoming += plan.mig_recv[q];
+  }
+  auto exchange = [&](void* buf, size_t elem) -> int {
+    size_t a[kMaxWorld], b[kMaxWorld], c2[kMaxWorld], d[kMaxWorld];
+    for (int q = 0; q < world; q++) { a[q] = sb[q] * elem; b[q] = so[q] * elem; c2[q] = rb[q] * elem; d[q] = ro[q] * elem; }
+    return comm->all_to_all_v(buf, a, b, buf, c2, d, s);
+  };
+  NB_TRY(exchange(posm, 16));
+  NB_TRY(exchange(vel, 16));
+  NB_TRY(exchange(acc, 16));     // a read-back after this step shows the acceleration the body got in it (Particles[i].Acceleration)
+  NB_TRY(exchange(ids, 4));
+  const int stay = plan.send_off[rank + 1] - plan.send_off[rank];
+  *next = BodySegs{plan.send_off[rank], stay, n};
+  *n_next = stay + (int)incoming;
+  *n_received = (int)incoming;
+  return 0;
+}
+
+// Read-back in the domain-split mode: every body's record travels to the rank that owns its ORIGINAL index slice
+// [first, first + n_slice) (n_per bodies per rank), which receives its rows in order: out[(id - first) * rec_words ...].
+// rec = n records of rec_words floats in the current local order. A collective.
+int bh_let_return(BHState& local, Comm* comm, const int32_t* ids, int n, int64_t n_per, const float* rec, int rec_words, float* out,
+                  int n_slice, int64_t first, cudaStream_t s, double* launches) {
+  Impl* m = impl_of(local);
+  const int world = comm->world(), rank = comm->rank();
+  const int64_t cap = std::max<int64_t>(std::max<int64_t>(n, n_slice), 1);
+  NB_TRY(ensure(m, (int)cap, s));
+  NB_TRY(let_ensure(m, world, 1024, s));
+  const size_t need = (size_t)cap * (size_t)(rec_words + 1) * 2;      // send staging + receive staging (records + ids)
+  if ((int64_t)need > m->cap_ret) {
+    NB_CUDA(cudaStreamSynchronize(s));
+    NB_TRY(realloc_dev(&m->ret, need));
+    m->cap_ret = (int64_t)need;
+  }
+  float* send_rec = m->ret;
+  int32_t* send_ids = reinterpret_cast<int32_t*>(send_rec + (size_t)cap * rec_words);
+  float* recv_rec = reinterpret_cast<float*>(send_ids + cap);
+  int32_t* recv_ids = reinterpret_cast<int32_t*>(recv_rec + (size_t)cap * rec_words);
+  const unsigned nb = (unsigned)ceil_div(std::max(n, 1), 256);
+  int sorted = 0;
+  if (n > 0) {
+    let_owner_kernel<<<nb, 256, 0, s>>>(ids, n, n_per, world, m->sort.keys[0]);
+    sorted = radix_sort_pairs(m->sort, n, 8, s, launches);
+    let_pack_records_kernel<<<nb, 256, 0, s>>>(m->sort.idx[sorted], n, rec, rec_words, ids, send_rec, send_ids);
+    *launches += 2;
+  }
+  let_offsets_kernel<<<1, 32, 0, s>>>(m->sort.keys[sorted], n, world, nullptr, m->send_off);
+  NB_TRY(comm->all_gather_bytes(m->send_off, m->all_off, (size_t)(world + 1) * 4, s));
+  std::vector<int> off((size_t)world * (world + 1));
+  NB_CUDA(cudaMemcpyAsync(off.data(), m->all_off, off.size() * 4, cudaMemcpyDeviceToHost, s));
+  NB_CUDA(cudaStreamSynchronize(s));
+  size_t sb[kMaxWorld], so[kMaxWorld], rb[kMaxWorld], ro[kMaxWorld];
+  int64_t total = 0;
+  for (int q = 0; q < world; q++) {
+    const int* mine = off.data() + (size_t)rank * (world + 1);
+    const int* theirs = off.data() + (size_t)q * (world + 1);
+    sb[q] = (size_t)(mine[q + 1] - mine[q]); so[q] = (size_t)mine[q];
+    rb[q] = (size_t)(theirs[rank + 1] - theirs[rank]); ro[q] = (size_t)total;
+    total += (int64_t)rb[q];
+  }
+  // all ranks see all offsets: a body count that does not add up fails everywhere, before the exchange
+  for (int d = 0; d < world; d++) {
+    int64_t t = 0;
+    for (int q = 0; q < world; q++) t += off[(size_t)q * (world + 1) + d + 1] - off[(size_t)q * (world + 1) + d];
+    const int64_t want = std::max<int64_t>(0, std::min<int64_t>(n_per, n_per * world - (int64_t)d * n_per));
+    if (t > want) { set_error("Barnes-Hut LET: read-back found " + std::to_string(t) + " bodies for the slice of rank " + std::to_string(d)); return -5; }
+  }
+  size_t a[kMaxWorld], b[kMaxWorld], c2[kMaxWorld], d2[kMaxWorld];
+  for (int q = 0; q < world; q++) { a[q] = sb[q] * rec_words * 4; b[q] = so[q] * rec_words * 4; c2[q] = rb[q] * rec_words * 4; d2[q] = ro[q] * rec_words * 4; }
+  NB_TRY(comm->all_to_all_v(send_rec, a, b, recv_rec, c2, d2, s));
+  for (int q = 0; q < world; q++) { a[q] = sb[q] * 4; b[q] = so[q] * 4; c2[q] = rb[q] * 4; d2[q] = ro[q] * 4; }
+  NB_TRY(comm->all_to_all_v(send_ids, a, b, recv_ids, c2, d2, s));
+  if (total > 0) {
+    let_unpack_records_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(recv_rec, recv_ids, (int)total, rec_words, first, n_slice, out);
+    *launches += 1;
+  }
+  NB_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // Diagnostics: every rank's bodies gathered into one array (n_global float4) - the energy sum needs all sources.
 int bh_let_gather_all(BHState& local, Comm* comm, const float4* posm, int n, int64_t n_global, const float4** out, int64_t* first,
@@ -1286,13 +1611,12 @@ int bh_read_tree(BHState& st, float* com4, int32_t* meta4, int32_t* range2, uint
 int sort_pairs_host(const uint64_t* keys_in, int64_t n, int key_bits, uint64_t* keys_out, uint32_t* idx_out, float* ms) {
   if (n <= 0 || n > (1ll << 30)) { set_error("sort: n out of range"); return -1; }
   RadixSortBuffers b;
-  const size_t nblocks = ceil_div(n, kSortTile);
   int rc = 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   auto body = [&]() -> int {
     for (int k = 0; k < 2; k++) { NB_TRY(realloc_dev(&b.keys[k], (size_t)n)); NB_TRY(realloc_dev(&b.idx[k], (size_t)n)); }
-    NB_TRY(realloc_dev(&b.hist, 256 * nblocks));
-    NB_TRY(realloc_dev(&b.tile_sums, ceil_div((int64_t)(256 * nblocks), kScanTile) + 1));
+    b.work_words = radix_work_words(n);
+    NB_TRY(realloc_dev(&b.work, b.work_words));
     NB_CUDA(cudaEventCreate(&e0));
     NB_CUDA(cudaEventCreate(&e1));
     float best = 1e30f;
@@ -1315,7 +1639,7 @@ int sort_pairs_host(const uint64_t* keys_in, int64_t n, int key_bits, uint64_t* 
   };
   rc = body();
   for (int k = 0; k < 2; k++) { cudaFree(b.keys[k]); cudaFree(b.idx[k]); }
-  cudaFree(b.hist); cudaFree(b.tile_sums);
+  cudaFree(b.work);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   return rc;

@@ -24,9 +24,27 @@ struct BHParams {
   int mac = kMacGroup;
   int group_size = 32;  // bodies per walk group: 32, 64 or 128 (1, 2 or 4 per lane)
   bool leave_sm_slot = false;  // walk with one CTA per SM fewer than fit, so kernels of another stream can run beside it
-  float let_time_weight = 0.f; // domain split: 0 = equal body counts per rank, up to 1 = equal last-step walk time
   int depth_hint = 0;          // last known tree depth (0 = unknown): how many key levels the sort has to resolve
   int group_pack = 2;   // cells of <= group_pack * group_size bodies are cut into equal walk groups
+  bool sticky_root = false;    // keep the previous root cube while it holds all bodies (multi-GPU domain split: keys stay comparable)
+  bool keep_root = false;      // the root cube is already in place (tree over received points: same cube as the local tree)
+  float let_damping = 0.5f;    // domain split: fraction of the way a splitter moves towards its new equal-work quantile per step
+};
+
+// Where the bodies of a build sit in the input arrays: logical body i is entry b0 + i for i < n0, else b1 + (i - n0).
+struct BodySegs {
+  int b0 = 0, n0 = 0x7fffffff, b1 = 0;
+  __host__ __device__ int at(int i) const { return i < n0 ? b0 + i : b1 + (i - n0); }
+};
+
+// What one step of the domain-split mode exchanges, known on the host after the step's one synchronisation.
+struct LetPlan {
+  int world = 1, rank = 0, n = 0;
+  int send_off[17] = {0};      // sorted bodies [send_off[q], send_off[q + 1]) belong to rank q under the current splitters
+  int mig_recv[16] = {0};      // bodies arriving from rank q
+  int let_send[16] = {0}, let_recv[16] = {0};   // locally-essential points to / from rank q
+  bool migrate = false;        // the migration fits the buffers of every rank
+  int64_t let_total = 0;
 };
 
 struct BHState {
@@ -44,7 +62,8 @@ void bh_iota(int32_t* ids, int n, int first, cudaStream_t s);
 // Sorts the n bodies along the Morton curve (*_in -> posm / vel / ids, which must not alias the inputs), builds the
 // tree over the sorted bodies and its monopoles. box = cube_size_kernel output (absmax, min xyz, max xyz).
 int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
-             float4* posm, float4* vel, int32_t* ids, int n, const uint32_t* box, cudaStream_t s, double* launches);
+             float4* posm, float4* vel, int32_t* ids, int n, const uint32_t* box, cudaStream_t s, double* launches,
+             const BodySegs* segs = nullptr);
 // Accelerations (G applied) of the sorted bodies [t0, t1) -> acc[t0 .. t1).
 int bh_forces(BHState& st, const BHParams& p, const float4* posm, float4* acc, int n, int t0, int t1, cudaStream_t s,
               double* launches);
@@ -55,11 +74,18 @@ int bh_forces_from(BHState& src, BHState& tgt_tree, const BHParams& p, const flo
 
 // ---- multi-GPU (K9): Morton domain split + body migration + locally-essential-tree exchange; see bh.cu
 class Comm;
-int bh_let_migrate(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
-                   float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, float walk_ms, int* n_local,
-                   cudaStream_t s, double* launches);
-int bh_let_exchange(BHState& local, BHState& let, Comm* comm, const BHParams& p, const float4* posm, int n,
-                    const uint32_t* box_global, int* n_let, cudaStream_t s, double* launches);
+void bh_let_forget_domains(BHState& st);
+int bh_let_redistribute(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
+                        float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local,
+                        cudaStream_t s, double* launches);
+int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* posm, int n, int64_t cap, LetPlan* plan, cudaStream_t s,
+                double* launches);
+int bh_let_import(BHState& local, BHState& let, Comm* comm, const BHParams& p, const LetPlan& plan, const uint32_t* box_global, int* n_let,
+                  cudaStream_t s, double* launches);
+int bh_let_finish(BHState& local, Comm* comm, const BHParams& p, const LetPlan& plan, float4* posm, float4* vel, float4* acc, int32_t* ids,
+                  BodySegs* next, int* n_next, int* n_received, cudaStream_t s, double* launches);
+int bh_let_return(BHState& local, Comm* comm, const int32_t* ids, int n, int64_t n_per, const float* rec, int rec_words, float* out,
+                  int n_slice, int64_t first, cudaStream_t s, double* launches);
 const float4* bh_let_sources(BHState& local);
 int bh_let_gather_all(BHState& local, Comm* comm, const float4* posm, int n, int64_t n_global, const float4** out, int64_t* first,
                       cudaStream_t s);

@@ -221,6 +221,18 @@ scatter_float4_kernel(const float4* __restrict__ in, const int32_t* __restrict__
   if (i < n) out[ids[i]] = in[i];
 }
 
+// Domain-split Barnes-Hut: after a migration the rank's bodies sit in two stretches (the ones that stayed, the ones that
+// arrived); a read-back first makes them contiguous again. b0/n0/b1: logical body i = b0 + i for i < n0, else b1 + (i - n0).
+__global__ void __launch_bounds__(256)
+compact_segments_kernel(const int b0, const int n0, const int b1, const int n, const float4* __restrict__ posm_in,
+                        const float4* __restrict__ vel_in, const float4* __restrict__ acc_in, const int32_t* __restrict__ ids_in,
+                        float4* __restrict__ posm_out, float4* __restrict__ vel_out, float4* __restrict__ acc_out, int32_t* __restrict__ ids_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = i < n0 ? b0 + i : b1 + (i - n0);
+  posm_out[i] = posm_in[j]; vel_out[i] = vel_in[j]; acc_out[i] = acc_in[j]; ids_out[i] = ids_in[j];
+}
+
 // out[0] = min, out[1] = max of the order-preserving keys of the masses (posm.w); initialise out = {~0, 0}.
 __global__ void __launch_bounds__(256)
 mass_range_kernel(const float4* __restrict__ posm, const int64_t n, uint32_t* __restrict__ out) {

@@ -108,6 +108,8 @@ struct nbody_sim {
   float4* d_vel2 = nullptr;  int64_t cap_vel2 = 0;
   int32_t* d_ids2 = nullptr; int64_t cap_ids2 = 0;
   uint8_t* d_stage = nullptr; int64_t cap_stage = 0;
+  float4* d_acc2 = nullptr; int64_t cap_acc2 = 0;      // domain split: destination of the accelerations when the bodies are compacted
+  float* d_ret = nullptr; int64_t cap_ret = 0;         // domain split: the rows of this rank's slice after a read-back
   uint32_t* d_box = nullptr;   // 8 words: absmax, min xyz, max xyz
   double* d_energy = nullptr;  // 2 doubles
   bool ids_identity = true;
@@ -121,6 +123,7 @@ struct nbody_sim {
   BHState tree_let;   // multi-GPU LET mode: tree over the points received from the peers
   int n_let = 0;
   int n_migrated = 0;
+  BodySegs segs;      // domain split: where this rank's bodies sit in d_posm / d_vel / d_ids before the next build
 
   // timing of the last call
   float ms_call = 0, ms_force = 0, ms_build = 0, ms_integrate = 0, ms_comm = 0;
@@ -293,11 +296,14 @@ int launch_cube_size(nbody_sim* s) {
   NB_CUDA(cudaMemcpyAsync(s->d_box, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
   // replicated Barnes-Hut keeps all N bodies on every rank: reduce over them locally, no collective
   const bool all_here = s->bh() && !s->let_mode();
-  const float4* src = all_here ? s->d_posm : s->posm_local();
-  const int64_t cnt = all_here ? s->n_global : s->n_local;
-  if (cnt > 0) {
-    const int blocks = (int)std::min<int64_t>(ceil_div(cnt, 256), kNumSMsB200 * 8);
-    cube_size_kernel<<<blocks, 256, 0, s->stream>>>(src, (int)cnt, s->d_box);
+  // domain split after a migration: the bodies that stayed and the ones that arrived are two stretches of the arrays
+  const bool two = s->let_mode() && s->segs.n0 < (int)s->n_local;
+  const float4* src[2] = {all_here ? s->d_posm : s->let_mode() ? s->d_posm + s->segs.b0 : s->posm_local(), s->d_posm + s->segs.b1};
+  const int64_t cnt[2] = {all_here ? s->n_global : two ? s->segs.n0 : s->n_local, two ? s->n_local - s->segs.n0 : 0};
+  for (int k = 0; k < 2; k++) {
+    if (cnt[k] <= 0) continue;
+    const int blocks = (int)std::min<int64_t>(ceil_div(cnt[k], 256), sm_count() * 8);
+    cube_size_kernel<<<blocks, 256, 0, s->stream>>>(src[k], (int)cnt[k], s->d_box);
     s->launches++;
     NB_CUDA(cudaGetLastError());
   }
@@ -339,59 +345,38 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
     bp.group_size = s->cfg.group_size;
     bp.group_pack = s->cfg.group_pack;
     bp.depth_hint = s->tree.depth_host;
-    if (const char* tw = getenv("NBODY_LET_TIME_WEIGHT")) bp.let_time_weight = std::min(1.f, std::max(0.f, (float)atof(tw)));   // development knob
+    if (const char* dm = getenv("NBODY_LET_DAMPING")) bp.let_damping = std::min(1.f, std::max(0.f, (float)atof(dm)));   // development knob
     double launches = 0;
     if (s->let_mode()) {
-      // (1)-(2) splitters + body migration, (3) local tree, (4)-(5) LET exchange + tree, (6) two walks; see bh.cu K9
+      // (1) local sort + tree, (2) plan: migration ranges, domain boxes, export descent, count exchange (the step's one host
+      // synchronisation), (3) LET exchange + tree beside the local walk, then the walk over the received points,
+      // (4) kick-drift, new splitters, lazy migration; see bh.cu K9
       // NBODY_LET_TRACE=1: synchronise after every phase and print host-clock phase times (development aid)
       static const bool trace = getenv("NBODY_LET_TRACE") != nullptr;
       auto t_prev = std::chrono::steady_clock::now();
       auto lap = [&](const char* what) {
         if (!trace) return;
         cudaStreamSynchronize(s->stream);
+        if (s->stream_x) cudaStreamSynchronize(s->stream_x);
         const auto now = std::chrono::steady_clock::now();
         fprintf(stderr, "[let rank %d step %lld] %-14s %8.3f ms  n_local=%lld n_let=%d\n", s->cfg.rank, (long long)s->steps, what,
                 std::chrono::duration<double, std::milli>(now - t_prev).count(), (long long)s->n_local, s->n_let);
         t_prev = now;
       };
+      bp.sticky_root = true;
       lap("cube");
-      // NBODY_LET_EVENTS=1: GPU timeline of the step from CUDA events on both streams (printed after a final sync)
-      static const bool evtrace = getenv("NBODY_LET_EVENTS") != nullptr;
-      std::vector<std::pair<const char*, cudaEvent_t>> marks;
-      auto mark = [&](const char* what, cudaStream_t st) {
-        if (!evtrace) return;
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.push_back({what, e});
-      };
-      mark("start(after cube)", s->stream);
-      int n_new = 0;
-      // device time of last step's walks on this rank = the weight of its domain in the next split (equal work per rank)
-      float walk_ms = 0.f;
-      if (s->ev_walk[0] && s->walk_timed) {
-        float a = 0.f, b = 0.f;
-        cudaEventSynchronize(s->ev_walk[3]);   // last step's walks (the migration below synchronises anyway)
-        if (cudaEventElapsedTime(&a, s->ev_walk[0], s->ev_walk[1]) == cudaSuccess &&
-            cudaEventElapsedTime(&b, s->ev_walk[2], s->ev_walk[3]) == cudaSuccess) walk_ms = a + b;
-        else cudaGetLastError();
-      }
-      NB_TRY(bh_let_migrate(s->tree, s->comm, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local,
-                            std::min(s->cap_posm, s->cap_posm2), s->d_box, walk_ms, &n_new, s->stream, &launches));
-      if (!s->ev_walk[0]) for (int q = 0; q < 4; q++) NB_CUDA(cudaEventCreate(&s->ev_walk[q]));
-      s->n_local = n_new;
-      lap("migrate");
-      mark("migrated", s->stream);
-      if (s->n_local > 0) {
-        NB_TRY(bh_build(s->tree, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local, s->d_box,
-                        s->stream, &launches));
-        std::swap(s->d_posm, s->d_posm2); std::swap(s->cap_posm, s->cap_posm2);
-        std::swap(s->d_vel, s->d_vel2);   std::swap(s->cap_vel, s->cap_vel2);
-        std::swap(s->d_ids, s->d_ids2);   std::swap(s->cap_ids, s->cap_ids2);
-      }
+      if (s->n_local <= 0) { set_error("Barnes-Hut domain split: a rank holds no bodies"); return NBODY_ERR_STATE; }
+      NB_TRY(bh_build(s->tree, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local, s->d_box,
+                      s->stream, &launches, &s->segs));
+      std::swap(s->d_posm, s->d_posm2); std::swap(s->cap_posm, s->cap_posm2);
+      std::swap(s->d_vel, s->d_vel2);   std::swap(s->cap_vel, s->cap_vel2);
+      std::swap(s->d_ids, s->d_ids2);   std::swap(s->cap_ids, s->cap_ids2);
+      s->segs = BodySegs{0, (int)s->n_local, 0};
       s->ids_identity = false;
       lap("local build");
-      mark("built", s->stream);
       if (ev) { NB_CUDA(cudaEventRecord(ev[1], s->stream)); NB_CUDA(cudaEventRecord(ev[5], s->stream)); }
-      // The local walk (stream) and the LET exchange + LET tree build (stream_x, incl. its host synchronisation for the
-      // list sizes) are independent: run them side by side; the walk of the received points waits for both.
+      // The local walk (stream) and the plan + LET exchange + LET tree build (stream_x, incl. the host synchronisation for
+      // the counts) are independent: run them side by side; the walk of the received points waits for both.
       if (!s->stream_x) {
         int lo = 0, hi = 0;
         NB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -401,53 +386,48 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       }
       const bool overlap = !trace && getenv("NBODY_LET_NO_OVERLAP") == nullptr;
       cudaStream_t sx = overlap ? s->stream_x : s->stream;
+      LetPlan plan;
+      const int64_t cap = std::min(std::min(s->cap_posm, s->cap_posm2), s->cap_acc);
       if (overlap) {
         NB_CUDA(cudaEventRecord(s->ev_built, s->stream));
         NB_CUDA(cudaStreamWaitEvent(sx, s->ev_built, 0));
         bp.leave_sm_slot = true;
-        NB_CUDA(cudaEventRecord(s->ev_walk[0], s->stream));
-        if (s->n_local > 0) NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
-        NB_CUDA(cudaEventRecord(s->ev_walk[1], s->stream));
-        mark("local walk done", s->stream);
-        mark("x: start", sx);
+        NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
       }
-      NB_TRY(bh_let_exchange(s->tree, s->tree_let, s->comm, bp, s->d_posm, (int)s->n_local, s->d_box, &s->n_let, sx, &launches));
-      lap("let exchange");
-      mark("x: exchanged + let tree", sx);
+      NB_TRY(bh_let_plan(s->tree, s->comm, bp, s->d_posm, (int)s->n_local, cap, &plan, sx, &launches));
+      lap("plan + export");
+      NB_TRY(bh_let_import(s->tree, s->tree_let, s->comm, bp, plan, s->d_box, &s->n_let, sx, &launches));
+      lap("let import");
       if (overlap) {
         NB_CUDA(cudaEventRecord(s->ev_let, sx));
         NB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_let, 0));
       } else {
-        NB_CUDA(cudaEventRecord(s->ev_walk[0], s->stream));
-        if (s->n_local > 0) NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
-        NB_CUDA(cudaEventRecord(s->ev_walk[1], s->stream));
+        NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
         lap("walk local");
       }
       bp.leave_sm_slot = false;
-      NB_CUDA(cudaEventRecord(s->ev_walk[2], s->stream));
-      if (s->n_local > 0 && s->n_let > 0)
+      if (s->n_let > 0)
         NB_TRY(bh_forces_from(s->tree_let, s->tree, bp, bh_let_sources(s->tree), s->d_posm, s->d_acc, s->n_let, 0, (int)s->n_local,
                               true, s->stream, &launches));
-      NB_CUDA(cudaEventRecord(s->ev_walk[3], s->stream));
-      s->walk_timed = true;
       lap("walk let");
-      mark("let walk done", s->stream);
-      if (evtrace) {
-        cudaStreamSynchronize(s->stream);
-        for (size_t k = 1; k < marks.size(); k++) {
-          float ms = 0; cudaEventElapsedTime(&ms, marks[0].second, marks[k].second);
-          fprintf(stderr, "[let-ev rank %d step %lld] %-26s @ %8.3f ms\n", s->cfg.rank, (long long)s->steps, marks[k].first, ms);
-        }
-        for (auto& mk : marks) cudaEventDestroy(mk.second);
-      }
-      s->launches += launches;
       if (ev) NB_CUDA(cudaEventRecord(ev[2], s->stream));
-      if (integrate && s->n_local > 0) {
+      if (integrate) {
         kick_drift_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>((int)s->n_local, dt, s->d_posm, s->d_vel, s->d_acc);
         s->launches++;
         NB_CUDA(cudaGetLastError());
       }
-      if (ev) { NB_CUDA(cudaEventRecord(ev[3], s->stream)); NB_CUDA(cudaEventRecord(ev[4], s->stream)); }
+      if (ev) NB_CUDA(cudaEventRecord(ev[3], s->stream));
+      if (integrate) {
+        // bodies that left this rank's key range move on AFTER the step (they were its targets in this step), the arrivals
+        // are appended; a pure force evaluation (CreateOctree) leaves everything where it is
+        int n_next = (int)s->n_local, n_recv = 0;
+        NB_TRY(bh_let_finish(s->tree, s->comm, bp, plan, s->d_posm, s->d_vel, s->d_acc, s->d_ids, &s->segs, &n_next, &n_recv, s->stream, &launches));
+        s->n_local = n_next;
+        s->n_migrated = n_recv;
+        lap("migrate");
+      }
+      s->launches += launches;
+      if (ev) NB_CUDA(cudaEventRecord(ev[4], s->stream));
       if (integrate) s->steps++;
       return 0;
     }
@@ -530,15 +510,72 @@ int finish_set(nbody_sim* s) {
     else bh_iota(s->d_ids, (int)s->n_global, 0, s->stream);
     s->launches++;
   }
-  bh_reset(s->tree, s->stream);
-  bh_reset(s->tree_let, s->stream);
   s->n_let = 0;
-  s->walk_timed = false;
+  s->n_migrated = 0;
+  s->segs = BodySegs{0, (int)s->n_local, 0};
+  if (s->let_mode()) {
+    // Domain split: the rank uploaded a slice of the caller's order; send every body to the rank that owns its stretch of
+    // the Morton curve now (a collective: all ranks set their bodies together). The root cube and the splitters of an
+    // earlier run are kept when they still fit - a caller that uploads the same system every frame pays one exchange,
+    // not a re-balancing from scratch.
+    const int depth_hint = s->tree.depth_host;
+    bh_reset(s->tree_let, s->stream);
+    s->tree.depth_host = depth_hint;
+    NB_TRY(launch_cube_size(s));
+    BHParams bp;
+    bp.sticky_root = true;
+    double launches = 0;
+    int n_new = 0;
+    NB_TRY(bh_let_redistribute(s->tree, s->comm, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local,
+                               std::min(std::min(s->cap_posm, s->cap_posm2), s->cap_acc), s->d_box, &n_new, s->stream, &launches));
+    s->launches += launches;
+    s->n_local = n_new;
+    s->segs = BodySegs{0, n_new, 0};
+    s->ids_identity = false;
+    if (n_new > 0) NB_CUDA(cudaMemsetAsync(s->d_acc, 0, (size_t)n_new * 16, s->stream));   // the uploaded accelerations stayed with the slice
+  } else {
+    bh_reset(s->tree, s->stream);
+    bh_reset(s->tree_let, s->stream);
+  }
   NB_TRY(publish_positions(s));
   NB_TRY(detect_equal_mass(s));
   NB_CUDA(cudaStreamSynchronize(s->stream));
   s->initialized = true;
   s->steps = 0;
+  return 0;
+}
+
+// Domain split: after a lazy migration the bodies sit in two stretches; everything that looks at the whole local set
+// (read-backs, energy, device pointers) first makes them contiguous again.
+int let_make_contiguous(nbody_sim* s) {
+  if (!s->let_mode() || (s->segs.b0 == 0 && s->segs.n0 >= (int)s->n_local)) return 0;
+  NB_TRY(dev_reserve(&s->d_acc2, &s->cap_acc2, s->cap_acc, s->stream));
+  if (s->n_local > 0) {
+    compact_segments_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(s->segs.b0, s->segs.n0, s->segs.b1, (int)s->n_local, s->d_posm, s->d_vel,
+                                                                                         s->d_acc, s->d_ids, s->d_posm2, s->d_vel2, s->d_acc2, s->d_ids2);
+    s->launches++;
+    NB_CUDA(cudaGetLastError());
+  }
+  std::swap(s->d_posm, s->d_posm2); std::swap(s->cap_posm, s->cap_posm2);
+  std::swap(s->d_vel, s->d_vel2);   std::swap(s->cap_vel, s->cap_vel2);
+  std::swap(s->d_ids, s->d_ids2);   std::swap(s->cap_ids, s->cap_ids2);
+  std::swap(s->d_acc, s->d_acc2);   std::swap(s->cap_acc, s->cap_acc2);
+  s->segs = BodySegs{0, (int)s->n_local, 0};
+  return 0;
+}
+
+// Domain-split read-back: every rank receives the rows of its slice of the caller's order (return to owner) into the
+// staging buffer, [n_slice][rec_words] floats. rec = the local records in their current order. A collective.
+int let_read_back(nbody_sim* s, const float* rec, int rec_words, float** out_dev, int64_t* n_slice_out) {
+  const int64_t n_slice = std::max<int64_t>(0, std::min<int64_t>(s->n_per, s->n_global - s->slice_begin));
+  NB_TRY(let_make_contiguous(s));
+  NB_TRY(dev_reserve(&s->d_ret, &s->cap_ret, std::max<int64_t>(n_slice, 1) * rec_words, s->stream));
+  double launches = 0;
+  NB_TRY(bh_let_return(s->tree, s->comm, s->d_ids, (int)s->n_local, s->n_per, rec, rec_words, s->d_ret, (int)n_slice, s->slice_begin,
+                       s->stream, &launches));
+  s->launches += launches;
+  *out_dev = s->d_ret;
+  *n_slice_out = n_slice;
   return 0;
 }
 
@@ -549,7 +586,16 @@ int get_array(nbody_sim* s, int what, float* out4, int64_t n) {
   if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
   if (!out4 || n < s->n_global) return invalid("output buffer is NULL or smaller than n_global bodies");
   NB_CUDA(cudaSetDevice(s->cfg.device));
+  NB_TRY(let_make_contiguous(s));
   const float4* src = what == 0 ? s->posm_local() : what == 1 ? s->vel_local() : s->acc_local();
+  if (s->let_mode()) {   // bodies live wherever their domain is: bring the rows of this rank's slice home, one copy out
+    float* rows = nullptr;
+    int64_t n_slice = 0;
+    NB_TRY(let_read_back(s, reinterpret_cast<const float*>(src), 4, &rows, &n_slice));
+    if (n_slice > 0) NB_CUDA(cudaMemcpyAsync(out4 + 4 * s->slice_begin, rows, (size_t)n_slice * 16, cudaMemcpyDeviceToHost, s->stream));
+    NB_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+  }
   if (s->n_local == 0) return 0;
   if (s->ids_identity) {
     NB_CUDA(cudaMemcpyAsync(out4 + 4 * s->identity_begin(), src, (size_t)s->n_local * 16, cudaMemcpyDeviceToHost, s->stream));
@@ -656,7 +702,7 @@ void nbody_destroy(nbody_sim* s) {
   bh_free(s->tree_let);
   cudaFree(s->d_posm2); cudaFree(s->d_vel2); cudaFree(s->d_ids2);
   cudaFree(s->d_posm); cudaFree(s->d_vel); cudaFree(s->d_acc); cudaFree(s->d_partial); cudaFree(s->d_ids);
-  cudaFree(s->d_stage); cudaFree(s->d_box); cudaFree(s->d_energy);
+  cudaFree(s->d_stage); cudaFree(s->d_ret); cudaFree(s->d_acc2); cudaFree(s->d_box); cudaFree(s->d_energy);
   for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -738,6 +784,7 @@ int nbody_clean_particles(nbody_sim* s) {
   s->n_global = s->n_local = 0;
   s->steps = 0;
   bh_reset(s->tree, s->stream);
+  bh_let_forget_domains(s->tree);
   return NBODY_OK;
 }
 
@@ -797,6 +844,25 @@ int nbody_get_particles_aos(nbody_sim* s, void* particles, int64_t n, size_t str
   if (!particles || n < s->n_global) return invalid("output buffer is NULL or smaller than n_global bodies");
   if (stride < sizeof(nbody_particle) || stride % 4) return invalid("stride must be >= 40 and a multiple of 4");
   NB_CUDA(cudaSetDevice(s->cfg.device));
+  if (s->let_mode()) {
+    NB_TRY(let_make_contiguous(s));
+    const size_t lbytes = (size_t)std::max<int64_t>(s->n_local, 1) * 40;
+    NB_TRY(stage_reserve(s, (int64_t)lbytes));
+    if (s->n_local > 0) {
+      soa_to_aos_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>(s->d_posm, s->d_vel, s->d_acc, (int)s->n_local, nullptr, reinterpret_cast<float*>(s->d_stage));
+      s->launches++;
+    }
+    float* rows = nullptr;
+    int64_t n_slice = 0;
+    NB_TRY(let_read_back(s, reinterpret_cast<const float*>(s->d_stage), 10, &rows, &n_slice));
+    uint8_t* dst0 = (uint8_t*)particles + (size_t)s->slice_begin * stride;
+    if (n_slice > 0) {
+      if (stride == 40) NB_CUDA(cudaMemcpyAsync(dst0, rows, (size_t)n_slice * 40, cudaMemcpyDeviceToHost, s->stream));
+      else NB_CUDA(cudaMemcpy2DAsync(dst0, stride, rows, 40, 40, (size_t)n_slice, cudaMemcpyDeviceToHost, s->stream));
+    }
+    NB_CUDA(cudaStreamSynchronize(s->stream));
+    return NBODY_OK;
+  }
   if (s->n_local == 0) return NBODY_OK;
   const size_t bytes = (size_t)s->n_local * 40;
   NB_TRY(stage_reserve(s, (int64_t)bytes));
@@ -829,6 +895,14 @@ int nbody_get_particles_aos(nbody_sim* s, void* particles, int64_t n, size_t str
 int nbody_get_local_ids(nbody_sim* s, int64_t* ids, int64_t cap, int64_t* n_local) {
   if (!s) return invalid("sim is NULL");
   if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
+  if (s->let_mode()) {   // the rows this rank's read-backs fill: its slice of the caller's order (return to owner)
+    const int64_t n_slice = std::max<int64_t>(0, std::min<int64_t>(s->n_per, s->n_global - s->slice_begin));
+    if (n_local) *n_local = n_slice;
+    if (!ids) return NBODY_OK;
+    if (cap < n_slice) return invalid("ids capacity too small");
+    for (int64_t i = 0; i < n_slice; i++) ids[i] = s->slice_begin + i;
+    return NBODY_OK;
+  }
   if (n_local) *n_local = s->n_local;
   if (!ids) return NBODY_OK;
   if (cap < s->n_local) return invalid("ids capacity too small");
@@ -885,6 +959,7 @@ int nbody_energy(nbody_sim* s, double* ke, double* pe) {
   if (!s) return invalid("sim is NULL");
   if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
   NB_CUDA(cudaSetDevice(s->cfg.device));
+  NB_TRY(let_make_contiguous(s));
   NB_CUDA(cudaMemsetAsync(s->d_energy, 0, 2 * sizeof(double), s->stream));
   // sources = all N bodies; local body i sits at source index first + i (what the self-pair exclusion needs). Direct and
   // replicated Barnes-Hut keep them in d_posm; in LET mode they are gathered from the ranks (a collective: every rank calls).
@@ -936,6 +1011,7 @@ int nbody_octree_boxes(nbody_sim* s, float* boxes7, int64_t cap, int64_t* n_boxe
 int nbody_device_ptrs(nbody_sim* s, void** posm4, void** vel4, void** acc4) {
   if (!s) return invalid("sim is NULL");
   if (!s->initialized) { set_error("not initialised"); return NBODY_ERR_STATE; }
+  NB_TRY(let_make_contiguous(s));
   if (posm4) *posm4 = s->posm_local();
   if (vel4) *vel4 = s->vel_local();
   if (acc4) *acc4 = s->acc_local();
@@ -1034,7 +1110,7 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, const float*
 
 extern "C" int nbody_measure_fp32_peak(int32_t device, double* tflops, double* sm_mhz) {
   NB_TRY(check_device(device));
-  const int blocks = kNumSMsB200 * 4, iters = 40000;
+  const int blocks = sm_count() * 4, iters = 40000;
   float *d_out = nullptr, *d_in = nullptr;
   long long* d_cyc = nullptr;
   NB_CUDA(cudaMalloc((void**)&d_out, (size_t)blocks * 256 * 4));

@@ -4,10 +4,13 @@
 // octree (Octree::Add, /root/reference/Source/NBody/OctreeSearch.h:60-81): sorting the bodies along the Morton curve
 // makes every octree cell a contiguous index range.
 //
-// 8 passes of 8 bits (fewer when the tree needs fewer levels). Per pass: (1) per-CTA digit histogram, (2) exclusive scan
-// of the digit-major table hist[digit][cta] (gives every CTA its global base per digit), (3) stable scatter of 4096-key
-// tiles staged in shared memory (see radix_scatter_kernel). All HBM-bound: per pass 8 B key read (hist) + 12 B read +
-// 12 B write (scatter) per body.
+// 8-bit digits, only the passes the tree needs. ONE kernel per pass ("onesweep"): a CTA takes the next 4096-key tile
+// (ticket from an atomic counter), ranks its keys among equal digits with warp ballots, publishes its per-digit counts
+// and finds its global offsets by a decoupled look-back over the tiles before it (one status word per tile and digit:
+// 2 flag bits + 30 count bits, so flag and value travel in one store), then writes the tile out through shared memory,
+// digit run by digit run, coalesced. The digit histogram a pass needs up front is produced by the pass before it (the
+// keys are in registers anyway); the first one comes from the kernel that generates the keys (or radix_hist_kernel).
+// HBM traffic per pass: 12 B read + 12 B written per body (+ 1 KB of status per tile).
 #pragma once
 #include <algorithm>
 
@@ -19,11 +22,8 @@ constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;                              // keys per thread
 constexpr int kSortTile = kSortThreads * kSortItems;        // 4096 keys per CTA
 constexpr int kSortWarps = kSortThreads / 32;
-
-// ---- exclusive scan of uint32 (three small kernels; n up to 2^31) --------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr int kSortMaxPasses = 8;
+constexpr uint32_t kStatusAggregate = 1u << 30, kStatusPrefix = 2u << 30, kStatusValue = (1u << 30) - 1u;
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 #pragma unroll
@@ -36,113 +36,62 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 
 // Block-wide exclusive scan of one value per thread (256 threads); returns the exclusive prefix, *total = block sum.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
-  __shared__ uint32_t wsum[kScanThreads / 32];
+  __shared__ uint32_t wsum[kSortWarps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t inc = warp_incl_scan(v);
   if (lane == 31) wsum[w] = inc;
   __syncthreads();
   if (w == 0) {
-    uint32_t s = lane < kScanThreads / 32 ? wsum[lane] : 0u;
+    uint32_t s = lane < kSortWarps ? wsum[lane] : 0u;
     s = warp_incl_scan(s);
-    if (lane < kScanThreads / 32) wsum[lane] = s;
+    if (lane < kSortWarps) wsum[lane] = s;
   }
   __syncthreads();
   const uint32_t base = w ? wsum[w - 1] : 0u;
-  *total = wsum[kScanThreads / 32 - 1];
+  *total = wsum[kSortWarps - 1];
   __syncthreads();
   return base + inc - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads)
-scan_tile_sums_kernel(const uint32_t* __restrict__ in, const int64_t n, uint32_t* __restrict__ tile_sums) {
-  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; k++) if (base + k < n) s += in[base + k];
-  uint32_t total;
-  block_excl_scan(s, &total);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-// One CTA: in-place exclusive scan of m tile sums (m is small: n / 2048).
-__global__ void __launch_bounds__(kScanThreads)
-scan_spine_kernel(uint32_t* __restrict__ tile_sums, const int64_t m) {
-  uint32_t carry = 0;
-  for (int64_t base = 0; base < m; base += kScanThreads) {
-    const int64_t i = base + threadIdx.x;
-    const uint32_t v = i < m ? tile_sums[i] : 0u;
-    uint32_t total;
-    const uint32_t ex = block_excl_scan(v, &total);
-    if (i < m) tile_sums[i] = carry + ex;
-    carry += total;
-  }
-}
-__global__ void __launch_bounds__(kScanThreads)
-scan_apply_kernel(uint32_t* __restrict__ data, const int64_t n, const uint32_t* __restrict__ tile_sums) {
-  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-  uint32_t v[kScanItems], s = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; k++) { v[k] = base + k < n ? data[base + k] : 0u; s += v[k]; }
-  uint32_t total;
-  uint32_t ex = block_excl_scan(s, &total) + tile_sums[blockIdx.x];
-#pragma unroll
-  for (int k = 0; k < kScanItems; k++) { if (base + k < n) data[base + k] = ex; ex += v[k]; }
-}
-
-// In-place exclusive scan; tile_sums must hold ceil(n / kScanTile) words. 3 launches.
-inline void exclusive_scan_u32(uint32_t* data, int64_t n, uint32_t* tile_sums, cudaStream_t s, double* launches) {
-  const int64_t tiles = ceil_div(n, kScanTile);
-  scan_tile_sums_kernel<<<(unsigned)tiles, kScanThreads, 0, s>>>(data, n, tile_sums);
-  scan_spine_kernel<<<1, kScanThreads, 0, s>>>(tile_sums, tiles);
-  scan_apply_kernel<<<(unsigned)tiles, kScanThreads, 0, s>>>(data, n, tile_sums);
-  if (launches) *launches += 3;
-}
-
-// ---- radix pass ---------------------------------------------------------------------------------------------
+// Histogram of one digit over all keys -> ghist[256] (zeroed by the caller). Only for sorts whose keys do not come out
+// of a kernel that can count on the way (the Morton-key kernel does).
 __global__ void __launch_bounds__(kSortThreads)
-radix_hist_kernel(const uint64_t* __restrict__ keys, const int n, const int shift, uint32_t* __restrict__ hist,
-                  const int nblocks) {
+radix_hist_kernel(const uint64_t* __restrict__ keys, const int n, const int shift, uint32_t* __restrict__ ghist) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const int base = blockIdx.x * kSortTile;
-  uint64_t key[kSortItems];
-#pragma unroll
-  for (int k = 0; k < kSortItems; k++) {
-    const int i = base + k * kSortThreads + threadIdx.x;
-    key[k] = i < n ? keys[i] : 0ull;
-  }
-#pragma unroll
-  for (int k = 0; k < kSortItems; k++) {
-    const int i = base + k * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&h[(uint32_t)(key[k] >> shift) & 255u], 1u);
-  }
+  for (int i = blockIdx.x * kSortThreads + threadIdx.x; i < n; i += gridDim.x * kSortThreads)
+    atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
   __syncthreads();
-  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+  if (h[threadIdx.x]) atomicAdd(ghist + threadIdx.x, h[threadIdx.x]);
 }
 
-// hist must already hold the exclusive scan of the digit-major table. idx_in == nullptr: payload = position (first pass).
-// Stable scatter in three steps: (1) every warp ranks its 512 keys among equal digits with warp ballots (round r,
-// lane l = memory order); (2) warp counts are prefixed over the CTA's warps and digit totals over the digits, which
-// gives each key its position in the CTA's sorted tile - the tile is staged in shared memory in that order; (3) the
-// staged tile is written out front to back, so consecutive threads write consecutive addresses within each digit run.
-constexpr int kSortSmemBytes = kSortTile * 12 + (kSortWarps * 256 + 3 * 256) * 4;
+// One pass. ghist = histogram of this pass' digit over all keys; ghist_next (may be NULL) receives the histogram of the
+// next pass' digit (shift_next); status = ntiles x 256 words, ticket = 1 word, all zeroed by the caller.
+// idx_in == nullptr: payload = position (first pass). Stable.
+constexpr int kSortSmemBytes = kSortTile * 12 + (kSortWarps * 256 + 4 * 256) * 4 + 16;
 
-__global__ void __launch_bounds__(kSortThreads)
-radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, const int n,
-                     const int shift, const uint32_t* __restrict__ hist, const int nblocks,
-                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+__global__ void __launch_bounds__(kSortThreads, 3)
+radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, const int n, const int shift,
+                      const uint32_t* __restrict__ ghist, uint32_t* __restrict__ ghist_next, const int shift_next,
+                      uint32_t* __restrict__ status, uint32_t* __restrict__ ticket, uint64_t* __restrict__ keys_out,
+                      uint32_t* __restrict__ idx_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* skey = reinterpret_cast<uint64_t*>(smem_raw);                       // [kSortTile]
+  uint64_t* skey = reinterpret_cast<uint64_t*>(smem_raw);                           // [kSortTile]
   uint32_t* sidx = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSortTile * 8);   // [kSortTile]
-  uint32_t* wcount = sidx + kSortTile;                                          // [kSortWarps][256]
-  uint32_t* dbase = wcount + kSortWarps * 256;                                  // [256] global base of digit d for this CTA
-  uint32_t* lbase = dbase + 256;                                                // [256] start of digit d inside the sorted tile
-  uint32_t* dtot = lbase + 256;                                                 // [256]
+  uint32_t* wcount = sidx + kSortTile;                                              // [kSortWarps][256]
+  uint32_t* dbase = wcount + kSortWarps * 256;                                      // [256] global position of digit d's first key of this tile
+  uint32_t* lbase = dbase + 256;                                                    // [256] start of digit d inside the sorted tile
+  uint32_t* hnext = lbase + 256;                                                    // [256] next pass' digit histogram of this tile
+  uint32_t* stile = hnext + 256;                                                    // [1]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) *stile = atomicAdd(ticket, 1u);
 #pragma unroll
   for (int k = 0; k < kSortWarps; k++) wcount[k * 256 + threadIdx.x] = 0;
+  hnext[threadIdx.x] = 0;
   __syncthreads();
-  const int seg = blockIdx.x * kSortTile + w * (32 * kSortItems);
+  const int tile = (int)*stile;
+  const int seg = tile * kSortTile + w * (32 * kSortItems);
   uint64_t key[kSortItems];
   uint32_t rank[kSortItems];
   // all 16 loads first (independent, one memory round trip), then the ranking rounds, which synchronise the warp
@@ -172,19 +121,40 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
     if (live && before == 0) wcount[w * 256 + d] = prev + __popc(peers);
     __syncwarp();
     rank[r] = prev + before;
+    if (ghist_next && live) atomicAdd(&hnext[(uint32_t)(key[r] >> shift_next) & 255u], 1u);
   }
   __syncthreads();
   uint32_t total_d;
-  {  // thread d: prefix the warp counts of digit d over the CTA's warps, fetch the global base
+  {  // thread d: prefix the warp counts of digit d over the CTA's warps
     uint32_t run = 0;
 #pragma unroll
     for (int k = 0; k < kSortWarps; k++) { const uint32_t t = wcount[k * 256 + threadIdx.x]; wcount[k * 256 + threadIdx.x] = run; run += t; }
     total_d = run;
-    dtot[threadIdx.x] = run;
-    dbase[threadIdx.x] = hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
   }
+  // publish this tile's count of digit d, then look back over the earlier tiles for the running total
+  uint32_t* mine = status + (size_t)tile * 256 + threadIdx.x;
+  uint32_t excl = 0;
+  if (tile == 0) {
+    __stcg(mine, kStatusPrefix | total_d);
+  } else {
+    __stcg(mine, kStatusAggregate | total_d);
+    const volatile uint32_t* look = status + (size_t)(tile - 1) * 256 + threadIdx.x;
+    while (true) {
+      const uint32_t v = *look;
+      if ((v >> 30) == 0u) continue;          // that tile has not published yet (it holds an earlier ticket: it is running)
+      excl += v & kStatusValue;
+      if (v & kStatusPrefix) break;
+      look -= 256;
+    }
+    __stcg(mine, kStatusPrefix | (excl + total_d));
+  }
+  // global base of digit d = number of keys with a smaller digit + keys of digit d in earlier tiles
+  uint32_t all;
+  const uint32_t gbase = block_excl_scan(ghist[threadIdx.x], &all);
+  dbase[threadIdx.x] = gbase + excl;
   uint32_t tile_total;
   lbase[threadIdx.x] = block_excl_scan(total_d, &tile_total);
+  if (ghist_next && hnext[threadIdx.x]) atomicAdd(ghist_next + threadIdx.x, hnext[threadIdx.x]);
   __syncthreads();
   uint32_t pay[kSortItems];
 #pragma unroll
@@ -215,29 +185,62 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
 struct RadixSortBuffers {
   uint64_t* keys[2] = {nullptr, nullptr};
   uint32_t* idx[2] = {nullptr, nullptr};
-  uint32_t* hist = nullptr;       // 256 * nblocks
-  uint32_t* tile_sums = nullptr;  // ceil(256 * nblocks / kScanTile)
+  uint32_t* work = nullptr;       // [kSortMaxPasses + 1][256] digit histograms | [16] tickets | [passes][ntiles][256] status
+  size_t work_words = 0;
 };
 
-// Sorts keys[0] (payload = iota) by bits [first_bit rounded down to a multiple of 8, key_bits); the result is in
-// keys[out], idx[out] (returned index). Lower bits keep their input order (stable).
-inline int radix_sort_pairs(RadixSortBuffers& b, int n, int key_bits, cudaStream_t s, double* launches, int first_bit = 0) {
-  const int nblocks = (int)ceil_div(n, kSortTile);
-  static const cudaError_t attr_rc = cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemBytes);
-  (void)attr_rc;
+inline size_t radix_work_words(int64_t n) {
+  const size_t ntiles = (size_t)ceil_div(std::max<int64_t>(n, 1), kSortTile);
+  return (size_t)(kSortMaxPasses + 1) * 256 + 16 + (size_t)kSortMaxPasses * ntiles * 256;
+}
+
+struct RadixPlan {
+  int p0 = 0, passes = 0;            // 8-bit passes p0 .. passes-1 (shift = 8 p)
+  uint32_t* ghist0 = nullptr;        // where the first pass expects its digit histogram
+  int shift0 = 0;
+};
+
+// Zeroes the work area for a sort of bits [first_bit rounded down to a multiple of 8, key_bits) and tells the producer of
+// the keys where to count the first digit.
+inline RadixPlan radix_sort_begin(RadixSortBuffers& b, int n, int key_bits, cudaStream_t s, int first_bit = 0) {
+  RadixPlan pl;
+  pl.passes = (key_bits + 7) / 8;
+  pl.p0 = std::max(0, std::min(first_bit / 8, pl.passes - 1));
+  const size_t ntiles = (size_t)ceil_div(n, kSortTile);
+  const size_t used = (size_t)(kSortMaxPasses + 1) * 256 + 16 + (size_t)(pl.passes - pl.p0) * ntiles * 256;
+  cudaMemsetAsync(b.work, 0, used * sizeof(uint32_t), s);
+  pl.ghist0 = b.work;
+  pl.shift0 = 8 * pl.p0;
+  return pl;
+}
+
+// Runs the passes; the histogram of the first digit must already be in pl.ghist0. The result is in keys[out], idx[out]
+// (returned index); payload = position in the input. Lower bits keep their input order (stable).
+inline int radix_sort_run(RadixSortBuffers& b, const RadixPlan& pl, int n, cudaStream_t s, double* launches) {
+  const int ntiles = (int)ceil_div(n, kSortTile);
+  cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemBytes);   // per device: cheap, idempotent
+  uint32_t* tickets = b.work + (size_t)(kSortMaxPasses + 1) * 256;
+  uint32_t* status = tickets + 16;
   int cur = 0;
-  const int passes = (key_bits + 7) / 8, p0 = std::max(0, std::min(first_bit / 8, passes - 1));
-  for (int p = p0; p < passes; p++) {
-    const int shift = 8 * p;
-    radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(b.keys[cur], n, shift, b.hist, nblocks);
-    if (launches) *launches += 1;
-    exclusive_scan_u32(b.hist, (int64_t)256 * nblocks, b.tile_sums, s, launches);
-    radix_scatter_kernel<<<nblocks, kSortThreads, kSortSmemBytes, s>>>(b.keys[cur], p == p0 ? nullptr : b.idx[cur], n, shift, b.hist, nblocks,
-                                                           b.keys[cur ^ 1], b.idx[cur ^ 1]);
+  for (int p = pl.p0; p < pl.passes; p++) {
+    const int k = p - pl.p0;
+    const bool last = p + 1 == pl.passes;
+    radix_onesweep_kernel<<<ntiles, kSortThreads, kSortSmemBytes, s>>>(
+        b.keys[cur], p == pl.p0 ? nullptr : b.idx[cur], n, 8 * p, b.work + (size_t)k * 256, last ? nullptr : b.work + (size_t)(k + 1) * 256,
+        8 * (p + 1), status + (size_t)k * ntiles * 256, tickets + k, b.keys[cur ^ 1], b.idx[cur ^ 1]);
     if (launches) *launches += 1;
     cur ^= 1;
   }
   return cur;
+}
+
+// Sorts keys[0] (payload = iota) by bits [first_bit rounded down to a multiple of 8, key_bits).
+inline int radix_sort_pairs(RadixSortBuffers& b, int n, int key_bits, cudaStream_t s, double* launches, int first_bit = 0) {
+  const RadixPlan pl = radix_sort_begin(b, n, key_bits, s, first_bit);
+  const int blocks = (int)std::min<int64_t>(ceil_div(n, kSortThreads * 8), sm_count() * 8);
+  radix_hist_kernel<<<std::max(blocks, 1), kSortThreads, 0, s>>>(b.keys[0], n, pl.shift0, pl.ghist0);
+  if (launches) *launches += 1;
+  return radix_sort_run(b, pl, n, s, launches);
 }
 
 }  // namespace nbody

@@ -69,16 +69,21 @@ def test_let_two_galaxies_forces_and_migration(world):
         with P.OctreeSearch(method=P.METHOD_BARNES_HUT, eps=eps, theta=theta, rank=r, world=world, nccl_unique_id=uid,
                             bh_exchange=0) as s:
             s.SetBodies(posm, vel)
-            ids_set = s.LocalIds()                    # before any step: the index slice this rank uploaded
-            pos_set = s.Positions()
+            ids_set = s.LocalIds()                    # the rows this rank's read-backs fill: its slice of the caller's order
+            pos_set = s.Positions()                   # read back before any step: the bodies already live in their domains
             s.CreateOctree()
             ids0 = s.LocalIds()
             acc0 = s.Accelerations()
             st0 = s.Stats()
-            s.Step(dt, steps)
+            moved, sizes = 0, [st0["n_local"]]
+            for _ in range(steps):                    # one step per call so that every step's migration count is seen
+                s.Step(dt, 1)
+                st = s.Stats()
+                moved += st["migrated"]
+                sizes.append(st["n_local"])
             ids = s.LocalIds()
             return dict(ids_set=ids_set, pos_set=pos_set, ids0=ids0, acc0=acc0, st0=st0, ids=ids, pos=s.Positions(),
-                        vel=s.Velocities(), acc=s.Accelerations(), st=s.Stats())
+                        vel=s.Velocities(), acc=s.Accelerations(), st=s.Stats(), moved=moved, sizes=sizes)
 
     out = run_ranks(world, rank_fn)
     # read-backs right after the upload land at the bodies' own rows (each rank holds a slice of the caller's order)
@@ -96,8 +101,11 @@ def test_let_two_galaxies_forces_and_migration(world):
     velc = combine(n, [(o["ids"], o["vel"]) for o in out])
     assert rel_l2(pos, pos1) <= 1e-4 and rel_l2(velc, vel1) <= 5e-3   # two Theta-0.35 walks, 6 steps of dt 0.02
     assert np.array_equal(pos[:, 3], posm[:, 3])                       # masses travelled with their bodies
-    moved = sum(len(np.setdiff1d(o["ids"], o["ids0"])) for o in out)
+    assert all(np.array_equal(o["ids"], o["ids_set"]) for o in out)   # read-backs return every body to its owner's rows
+    moved = sum(o["moved"] for o in out)
     assert moved > 0, "no body migrated: the test does not exercise the migration path"
+    for k in range(steps + 1):
+        assert sum(o["sizes"][k] for o in out) == n                   # no body lost or duplicated in any step
     acc_end = combine(n, [(o["ids"], o["acc"]) for o in out])
     assert np.all(np.isfinite(acc_end))
 
@@ -124,8 +132,8 @@ def test_let_theta0_is_the_direct_sum():
     out = run_ranks(world, rank_fn)
     acc = combine(n, [(o[0], o[1]) for o in out])
     assert rel_l2(acc, exact) <= 1e-5
-    for ids, _, st in out:
-        assert st["let_points"] == n - len(ids)
+    for _, _, st in out:
+        assert st["let_points"] == n - st["n_local"]
     assert sum(o[2]["interactions"] for o in out) == float(n) * n
 
 
@@ -187,3 +195,47 @@ def test_loopback_direct_and_replicated_are_bit_identical(method, exchange):
         assert np.array_equal(pos, pos1) and np.array_equal(velc, vel1)      # same tree, same groups
     else:
         assert rel_l2(pos, pos1) <= 1e-7 and rel_l2(velc, vel1) <= 2e-6      # same kernel, another j-split
+
+
+def test_let_upload_tick_readback_every_frame():
+    """The end-to-end pattern of a host application (and of bench.py's e2e leg): FParticle array in, Tick, FParticle array
+    out, every frame. Each upload re-uses the domains of the frame before (kept splitters and root cube); results follow
+    a single GPU doing the same."""
+    import parallelnbody_b200 as P
+    from parallelnbody_b200 import ic
+    n, eps, world, frames = 40_003, 0.01, 4, 4
+    posm, vel = ic.two_galaxies(n, seed=11)
+    start = P.api.to_particles(posm, vel)
+    with P.OctreeSearch(method=P.METHOD_BARNES_HUT, eps=eps, theta=0.3, PhDeltaTime=0.01) as one:
+        cur = start.copy()
+        for _ in range(frames):
+            one.Particles = cur
+            one.Tick()
+            cur = one.Particles
+        want = cur
+
+    def rank_fn(r, uid):
+        with P.OctreeSearch(method=P.METHOD_BARNES_HUT, eps=eps, theta=0.3, PhDeltaTime=0.01, rank=r, world=world,
+                            nccl_unique_id=uid, bh_exchange=0) as s:
+            cur = start.copy()
+            for _ in range(frames):
+                s.Particles = cur
+                s.Tick()
+                mine = s.Particles
+                ids = s.LocalIds()
+                # a real multi-process caller would all-gather the shares; the threads of this test share the array
+                shared[ids] = mine[ids]
+                barrier.wait()
+                cur = shared.copy()
+                barrier.wait()
+            return ids
+
+    import threading
+    shared = np.zeros(n, P.PARTICLE_DTYPE)
+    barrier = threading.Barrier(world)
+    out = run_ranks(world, rank_fn)
+    assert sum(len(i) for i in out) == n
+    assert np.array_equal(shared["Mass"], want["Mass"])
+    assert rel_l2(shared["Position"], want["Position"]) <= 1e-5
+    assert rel_l2(shared["Velocity"], want["Velocity"]) <= 5e-3
+    assert rel_l2(shared["Acceleration"], want["Acceleration"]) <= 2e-2     # two Theta-0.3 evaluations of the same field
