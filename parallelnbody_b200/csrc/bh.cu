@@ -17,6 +17,9 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "comm.h"
@@ -41,7 +44,6 @@ constexpr int kListCap = 128;            // per-warp interaction ring in shared 
 constexpr int kFlush = 64;               // pending entries evaluated per flush (the ring also holds up to 32 more + 31 left over)
 constexpr int kLeafChunk = 1 << 16;      // leaves at least this large are streamed on their own (bounds the packed scan of the walk)
 constexpr int kLetSamples = 256;         // key samples per rank for the domain splitters
-constexpr int kLetBoxes = 64;            // boxes describing a rank's domain to its peers
 constexpr int kMaxWorld = 16;
 constexpr int kCostBins = 1024;          // equal-count bins along the sorted bodies in which the walks record their work
 
@@ -75,8 +77,8 @@ struct Impl {
   uint64_t* splitters = nullptr;   // [world + 1] first key of every rank's domain (0 ... ~0)
   int* send_off = nullptr;         // [2 world + 1] body ranges per destination rank | export counts per peer
   int* all_off = nullptr;          // [world * (2 world + 1)] every rank's message
-  float* peer_boxes = nullptr;     // [world * kLetBoxes * 6] (min xyz, max xyz) of each rank's domain cells
-  int2* cut = nullptr;             // [kLetBoxes] body ranges of the local tree cells behind this rank's boxes
+  char* peer_pub = nullptr;        // [world * kPubBytes] every rank's published boundary tree (cells + bounding boxes)
+  int* pub_node = nullptr;         // [kLetPub] local tree node behind each published cell
   uint32_t* visit = nullptr;       // per node: which peers still descend through it
   int64_t cap_visit = 0;
   float4* let_out = nullptr;       // [world * cap_let] per-peer export lists
@@ -774,7 +776,7 @@ void bh_free(BHState& st) {
   cudaFree(m->sort.work);
   cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->groups); cudaFree(m->group_cost);
   cudaFree(m->counters); cudaFree(m->root); cudaFree(m->stacks); cudaFree(m->boxes);
-  cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_boxes); cudaFree(m->cut);
+  cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_pub); cudaFree(m->pub_node);
   cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->bin_cost); cudaFree(m->ret); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);
   delete m;
   st.impl = nullptr;
@@ -801,7 +803,7 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
   // whatever it holds, so a too-small hint costs accuracy nothing, only walk efficiency, and corrects itself through
   // the depth statistic). The parity configurations (one-body leaves / per-body walk) always sort all 63 bits.
   int levels = kMaxLevel;
-  if (p.leaf_size > 1 && p.mac == kMacGroup && p.depth_hint > 0) levels = std::min(kMaxLevel, std::max(10, p.depth_hint + 4));
+  if (p.leaf_size > 1 && p.mac == kMacGroup && p.depth_hint > 0 && !getenv("NBODY_FULL_SORT")) levels = std::min(kMaxLevel, std::max(10, p.depth_hint + 4));
   const RadixPlan plan = radix_sort_begin(m->sort, n, 3 * kMaxLevel, s, 3 * (kMaxLevel - levels));
   const unsigned nbk = (unsigned)std::min<int64_t>(nb, (int64_t)sm_count() * 16);   // grid-stride: few histogram flushes per CTA
   morton_kernel<<<nbk, 256, 0, s>>>(posm_in, n, m->root, m->sort.keys[0], plan.ghist0, plan.shift0, segs);
@@ -1081,60 +1083,73 @@ __global__ void let_offsets_kernel(const uint64_t* __restrict__ sorted, const in
   send_off[r] = lo;
 }
 
-// A rank describes its domain to its peers by the bounding boxes of a CUT of its local tree: starting from the root,
-// the cell with the most bodies is replaced by its children until kLetBoxes cells are reached. Tree cells are spatially
-// compact (a Morton range is not: it can jump across the whole cube), so the boxes hug the bodies. One warp: the
-// candidates live one per lane (two per lane for the second half), the arg-max is a warp reduction.
-__global__ void __launch_bounds__(32)
-let_cut_kernel(const int4* __restrict__ meta, const int2* __restrict__ range, const int n, int2* __restrict__ cut) {
-  __shared__ int node[kLetBoxes];
-  __shared__ int bodies[kLetBoxes];   // bodies of an internal candidate, 0 for leaves (never split)
-  const int lane = threadIdx.x;
-  int cnt = 0;
-  if (n > 0) {
-    if (lane == 0) { node[0] = 0; const int4 m = meta[0]; bodies[0] = (m.z & kLeafFlag) ? 0 : n; }
-    cnt = 1;
+// A rank describes its domain to its peers by the TOP OF ITS TREE ("boundary tree"): every cell whose parent holds more
+// than T bodies, with the bounding box of its bodies. Tree cells are spatially compact (a Morton range is not: it can jump
+// across the whole cube) and the description refines where the bodies are dense. Layout of the message (kPubBytes per rank):
+//   int header[32]: [0] = number of published cells, [1] = number of levels, [2 + l] = first cell of level l
+//   int2 child[kLetPub]: (first published child, number of children), (0, 0) for the leaves of the published tree
+//   float box[kLetPub][6]: min xyz, max xyz of the cell's bodies
+constexpr int kLetPub = 8192;
+constexpr int kPubLevels = 28;
+constexpr size_t kPubBytes = 32 * 4 + (size_t)kLetPub * 8 + (size_t)kLetPub * 24;
+__host__ __device__ inline const int* pub_header(const void* msg) { return reinterpret_cast<const int*>(msg); }
+__host__ __device__ inline const int2* pub_child(const void* msg) { return reinterpret_cast<const int2*>(reinterpret_cast<const char*>(msg) + 128); }
+__host__ __device__ inline const float* pub_box(const void* msg) { return reinterpret_cast<const float*>(reinterpret_cast<const char*>(msg) + 128 + (size_t)kLetPub * 8); }
+
+// One CTA: breadth-first from the root; a published cell with more than T bodies publishes its children (contiguous).
+__global__ void __launch_bounds__(1024)
+let_publish_kernel(const int4* __restrict__ meta, const int2* __restrict__ range, const int n, const int T, int* __restrict__ pub_node,
+                   void* __restrict__ msg) {
+  int* header = reinterpret_cast<int*>(msg);
+  int2* child = reinterpret_cast<int2*>(reinterpret_cast<char*>(msg) + 128);
+  __shared__ int s_count, s_valid;
+  if (threadIdx.x == 0) { s_count = n > 0 ? 1 : 0; s_valid = s_count; pub_node[0] = 0; header[2] = 0; }
+  __syncthreads();
+  int lb = 0, le = s_valid, level = 0;     // cells of `level` = [lb, le)
+  while (lb < le) {
+    const bool last = level + 1 == kPubLevels;
+    for (int i = lb + threadIdx.x; i < le; i += blockDim.x) {
+      const int node = pub_node[i];
+      const int4 m = meta[node];
+      const int2 r = range[node];
+      int2 ch = make_int2(0, 0);
+      if (!last && !(m.z & kLeafFlag) && r.y - r.x > T) {
+        const int slot = atomicAdd(&s_count, m.y);
+        if (slot + m.y <= kLetPub) {      // allocations are handed out in order: the ones that fit form a contiguous prefix
+          ch = make_int2(slot, m.y);
+          for (int k = 0; k < m.y; k++) pub_node[slot + k] = m.x + k;
+          atomicMax(&s_valid, slot + m.y);
+        }
+      }
+      child[i] = ch;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) header[2 + level + 1] = le;
+    lb = le;
+    le = s_valid;
+    level++;
+    __syncthreads();
   }
-  __syncwarp();
-  while (cnt > 0 && cnt < kLetBoxes) {
-    // candidate with the most bodies whose children still fit
-    int best = -1, bb = 1;
-    for (int k = lane; k < cnt; k += 32) {
-      const int b = bodies[k];
-      if (b > bb && cnt - 1 + meta[node[k]].y <= kLetBoxes) { best = k; bb = b; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int ob = __shfl_xor_sync(0xffffffffu, bb, o), ok = __shfl_xor_sync(0xffffffffu, best, o);
-      if (ob > bb || (ob == bb && ok >= 0 && (best < 0 || ok < best))) { bb = ob; best = ok; }
-    }
-    if (best < 0) break;
-    const int4 m = meta[node[best]];
-    __syncwarp();
-    if (lane < m.y) {
-      const int child = m.x + lane, slot = lane == 0 ? best : cnt + lane - 1;
-      const int4 cm = meta[child];
-      const int2 cr = range[child];
-      node[slot] = child;
-      bodies[slot] = (cm.z & kLeafFlag) ? 0 : cr.y - cr.x;
-    }
-    cnt += m.y - 1;
-    __syncwarp();
-  }
-  for (int k = lane; k < kLetBoxes; k += 32) cut[k] = k < cnt ? range[node[k]] : make_int2(0, 0);
+  if (threadIdx.x == 0) { header[0] = lb; header[1] = level; }
 }
 
-// Box b = bounding box of the bodies of cut cell b; unused entries get an inverted box that is infinitely far from
-// everything.
+// One CTA per published cell: the leaves of the published tree get the bounding box of their bodies, the inner cells an
+// empty box (filled bottom-up by let_pub_union_kernel).
 __global__ void __launch_bounds__(256)
-let_boxes_kernel(const float4* __restrict__ posm, const int2* __restrict__ cut, float* __restrict__ boxes6) {
+let_pub_boxes_kernel(const float4* __restrict__ posm, const int2* __restrict__ range, const int* __restrict__ pub_node, void* __restrict__ msg) {
   const int b = blockIdx.x;
-  const int lo = cut[b].x, hi = cut[b].y;
+  const int* header = reinterpret_cast<const int*>(msg);
+  if (b >= header[0]) return;
+  const int2 ch = reinterpret_cast<const int2*>(reinterpret_cast<const char*>(msg) + 128)[b];
+  float* box = reinterpret_cast<float*>(reinterpret_cast<char*>(msg) + 128 + (size_t)kLetPub * 8) + (size_t)b * 6;
   float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const float4 p = posm[i];
-    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
-    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  if (ch.y == 0) {
+    const int2 r = range[pub_node[b]];
+    for (int i = r.x + threadIdx.x; i < r.y; i += blockDim.x) {
+      const float4 p = posm[i];
+      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
   }
   __shared__ float s[8][6];
 #pragma unroll
@@ -1148,28 +1163,77 @@ let_boxes_kernel(const float4* __restrict__ posm, const int2* __restrict__ cut, 
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int q = 1; q < 8; q++) for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], s[q][k]); mx[k] = fmaxf(mx[k], s[q][3 + k]); }
-    for (int k = 0; k < 3; k++) { boxes6[b * 6 + k] = mn[k]; boxes6[b * 6 + 3 + k] = mx[k]; }
+    for (int k = 0; k < 3; k++) { box[k] = mn[k]; box[3 + k] = mx[k]; }
   }
 }
 
+// One CTA: inner cells = union of their children, level by level from the bottom.
+__global__ void __launch_bounds__(1024)
+let_pub_union_kernel(void* __restrict__ msg) {
+  const int* header = reinterpret_cast<const int*>(msg);
+  const int2* child = reinterpret_cast<const int2*>(reinterpret_cast<const char*>(msg) + 128);
+  float* box = reinterpret_cast<float*>(reinterpret_cast<char*>(msg) + 128 + (size_t)kLetPub * 8);
+  const int levels = header[1];
+  for (int l = levels - 2; l >= 0; l--) {
+    const int lb = header[2 + l], le = header[2 + l + 1];
+    for (int i = lb + threadIdx.x; i < le; i += blockDim.x) {
+      const int2 ch = child[i];
+      if (ch.y == 0) continue;
+      float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+      for (int k = 0; k < ch.y; k++)
+        for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], box[(size_t)(ch.x + k) * 6 + a]); mx[a] = fmaxf(mx[a], box[(size_t)(ch.x + k) * 6 + 3 + a]); }
+      for (int a = 0; a < 3; a++) { box[(size_t)i * 6 + a] = mn[a]; box[(size_t)i * 6 + 3 + a] = mx[a]; }
+    }
+    __syncthreads();
+  }
+}
+
+// Is the point mass (cm, cell half-width^2 / theta^2 = need) acceptable for EVERY body of a peer? Descends the peer's
+// published tree: a published cell whose box is farther than the acceptance distance settles all bodies inside it; a
+// published leaf that is too close settles the answer (no). The nearest child is visited first, so a "no" is found fast.
+__device__ __forceinline__ bool let_accept_for_peer(const float4 cm, const float need, const void* __restrict__ msg) {
+  const int npub = pub_header(msg)[0];
+  if (npub <= 0) return true;                       // the peer holds no bodies
+  const int2* child = pub_child(msg);
+  const float* box = pub_box(msg);
+  auto dist2 = [&](const int b) {
+    const float* bx = box + (size_t)b * 6;
+    const float dx = fmaxf(fmaxf(bx[0] - cm.x, cm.x - bx[3]), 0.f), dy = fmaxf(fmaxf(bx[1] - cm.y, cm.y - bx[4]), 0.f),
+                dz = fmaxf(fmaxf(bx[2] - cm.z, cm.z - bx[5]), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+  };
+  if (dist2(0) > need) return true;
+  int stack[96];
+  int sp = 0;
+  stack[sp++] = 0;
+  while (sp > 0) {
+    const int b = stack[--sp];
+    const int2 ch = child[b];
+    if (ch.y == 0) return false;                    // too close to a cell the peer does not describe any finer
+    // children that are still too close, nearest last (= popped first)
+    float dk[8];
+    int nk = 0, idx[8];
+    for (int k = 0; k < ch.y; k++) {
+      const float d = dist2(ch.x + k);
+      if (d > need) continue;
+      int q = nk++;
+      while (q > 0 && dk[q - 1] < d) { dk[q] = dk[q - 1]; idx[q] = idx[q - 1]; q--; }
+      dk[q] = d; idx[q] = ch.x + k;
+    }
+    if (sp + nk > 96) return false;                 // cannot happen for a 21-level tree; stay conservative
+    for (int k = 0; k < nk; k++) stack[sp++] = idx[k];
+  }
+  return true;
+}
+
 // The export descent, all peers at once, all generations in one cooperative launch. visit[node] = bit mask of the
-// peers that reached this node (written by the parent one generation earlier). A peer's boxes are tested hull first:
-// a cell accepted against the hull of all its boxes is accepted against each of them.
+// peers that reached this node (written by the parent one generation earlier).
 __global__ void __launch_bounds__(256)
 let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com,
                   const int4* __restrict__ node_meta, const Counters* __restrict__ c, const float4* __restrict__ root,
-                  const float* __restrict__ peer_boxes, const int world, const int rank, const float theta2,
+                  const char* __restrict__ peer_pub, const int world, const int rank, const float theta2,
                   uint32_t* __restrict__ visit, float4* __restrict__ let_out, int* __restrict__ let_cnt, const int cap_let) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ float hull[kMaxWorld][6];
-  if (threadIdx.x < world) {
-    const float* bx = peer_boxes + (size_t)threadIdx.x * kLetBoxes * 6;
-    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (int b = 0; b < kLetBoxes; b++)
-      for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], bx[b * 6 + k]); mx[k] = fmaxf(mx[k], bx[b * 6 + 3 + k]); }
-    for (int k = 0; k < 3; k++) { hull[threadIdx.x][k] = mn[k]; hull[threadIdx.x][3 + k] = mx[k]; }
-  }
-  __syncthreads();
   const float root_half = root[0].w;
   for (int gen = 0; gen <= kMaxLevel; gen++) {
   const int gb = c->gen_off[gen], ge = c->gen_off[gen + 1];
@@ -1182,27 +1246,11 @@ let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ no
     if (mask) {
       const float4 cm = node_com[node];
       const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);
-      const float need = size * size / fmaxf(theta2, 1e-30f);      // accepted  <=>  dmin^2 > need
+      const float need = size * size / fmaxf(theta2, 1e-30f);      // accepted  <=>  distance^2 > need
       const bool single = leaf && m.y == 1;
       for (int p = 0; p < world; p++) {
         if (!(mask >> p & 1u)) continue;
-        bool accept = single;
-        if (!accept) {
-          const float hx = fmaxf(fmaxf(hull[p][0] - cm.x, cm.x - hull[p][3]), 0.f), hy = fmaxf(fmaxf(hull[p][1] - cm.y, cm.y - hull[p][4]), 0.f),
-                      hz = fmaxf(fmaxf(hull[p][2] - cm.z, cm.z - hull[p][5]), 0.f);
-          accept = theta2 > 0.f && hx * hx + hy * hy + hz * hz > need;
-          if (!accept && theta2 > 0.f) {
-            const float* bx = peer_boxes + (size_t)p * kLetBoxes * 6;
-            float dmin2 = 3.0e38f;
-            for (int b = 0; b < kLetBoxes; b++) {
-              const float dx = fmaxf(fmaxf(bx[b * 6] - cm.x, cm.x - bx[b * 6 + 3]), 0.f);
-              const float dy = fmaxf(fmaxf(bx[b * 6 + 1] - cm.y, cm.y - bx[b * 6 + 4]), 0.f);
-              const float dz = fmaxf(fmaxf(bx[b * 6 + 2] - cm.z, cm.z - bx[b * 6 + 5]), 0.f);
-              dmin2 = fminf(dmin2, dx * dx + dy * dy + dz * dz);
-            }
-            accept = dmin2 > need;
-          }
-        }
+        const bool accept = single || (theta2 > 0.f && let_accept_for_peer(cm, need, peer_pub + (size_t)p * kPubBytes));
         if (accept) {
           const int slot = atomicAdd(let_cnt + p, 1);
           if (slot < cap_let) let_out[(size_t)p * cap_let + slot] = cm;
@@ -1252,8 +1300,8 @@ int let_ensure(Impl* m, int world, int64_t cap_local, cudaStream_t s) {
     NB_TRY(realloc_dev(&m->splitters, (size_t)world + 1));
     NB_TRY(realloc_dev(&m->send_off, (size_t)2 * world + 2));
     NB_TRY(realloc_dev(&m->all_off, (size_t)world * (2 * world + 2)));
-    NB_TRY(realloc_dev(&m->peer_boxes, (size_t)world * kLetBoxes * 6));
-    NB_TRY(realloc_dev(&m->cut, (size_t)kLetBoxes));
+    NB_TRY(realloc_dev(&m->peer_pub, (size_t)world * kPubBytes));
+    NB_TRY(realloc_dev(&m->pub_node, (size_t)kLetPub));
     NB_TRY(realloc_dev(&m->bin_cost, (size_t)kCostBins));
     NB_CUDA(cudaMemsetAsync(m->bin_cost, 0, kCostBins * sizeof(uint32_t), s));
     m->let_cnt = m->send_off + world + 1;      // the per-step count message: [world + 1] send_off | [world] export counts
@@ -1286,7 +1334,7 @@ void bh_let_forget_domains(BHState& st) { if (st.impl) static_cast<Impl*>(st.imp
 // Splitters from an earlier run of this handle are reused (the caller uploads the same system again: the domains are
 // already balanced for it); otherwise they are equal-count quantiles of regular key samples.
 int bh_let_redistribute(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
-                        float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local,
+                        float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local, int* n_stay,
                         cudaStream_t s, double* launches) {
   Impl* m = impl_of(st);
   const int world = comm->world(), rank = comm->rank();
@@ -1348,6 +1396,7 @@ int bh_let_redistribute(BHState& st, Comm* comm, const BHParams& p, float4* posm
   NB_TRY(exchange(vel_b, vel_a, 16));
   NB_TRY(exchange(ids_b, ids_a, 4));
   *n_local = (int)total;
+  *n_stay = (int)rb[rank];
   NB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1365,18 +1414,19 @@ int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* pos
     NB_TRY(realloc_dev(&m->visit, (size_t)need_nodes));
     m->cap_visit = need_nodes;
   }
-  // where the sorted bodies go under the current splitters
-  let_offsets_kernel<<<1, 32, 0, s>>>(m->sort.keys[m->sorted], n, world, m->splitters, m->send_off);
-  float* my_boxes = m->peer_boxes + (size_t)rank * kLetBoxes * 6;
-  let_cut_kernel<<<1, 32, 0, s>>>(m->node_meta, m->node_range, n, m->cut);
-  let_boxes_kernel<<<kLetBoxes, 256, 0, s>>>(posm, m->cut, my_boxes);
+  NB_CUDA(cudaMemsetAsync(m->send_off, 0, (size_t)(world + 1) * 4, s));
+  // this rank's boundary tree: cells whose parent holds more than n / 1024 bodies, with their bounding boxes
+  char* my_pub = m->peer_pub + (size_t)rank * kPubBytes;
+  let_publish_kernel<<<1, 1024, 0, s>>>(m->node_meta, m->node_range, n, std::max(64, n / 1024), m->pub_node, my_pub);
+  let_pub_boxes_kernel<<<kLetPub, 256, 0, s>>>(posm, m->node_range, m->pub_node, my_pub);
+  let_pub_union_kernel<<<1, 1024, 0, s>>>(my_pub);
   *launches += 3;
-  NB_TRY(comm->all_gather_bytes(my_boxes, m->peer_boxes, (size_t)kLetBoxes * 6 * 4, s));
+  NB_TRY(comm->all_gather_bytes(my_pub, m->peer_pub, kPubBytes, s));
   NB_CUDA(cudaMemsetAsync(m->let_cnt, 0, (size_t)world * 4, s));
   if (n > 0) {
     int w = world, r = rank, cap_let = (int)m->cap_let;
     float theta2 = p.theta * p.theta;
-    void* args[] = {(void*)&posm, &m->node_com, &m->node_meta, &m->counters, &m->root, &m->peer_boxes, &w, &r, &theta2, &m->visit,
+    void* args[] = {(void*)&posm, &m->node_com, &m->node_meta, &m->counters, &m->root, &m->peer_pub, &w, &r, &theta2, &m->visit,
                     &m->let_out, &m->let_cnt, &cap_let};
     NB_CUDA(cudaLaunchCooperativeKernel((void*)let_export_kernel, dim3(sm_count()), dim3(256), args, 0, s));
     *launches += 1;
@@ -1388,6 +1438,17 @@ int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* pos
   NB_CUDA(cudaMemcpyAsync(all.data(), m->all_off, all.size() * 4, cudaMemcpyDeviceToHost, s));
   NB_CUDA(cudaStreamSynchronize(s));
   plan->world = world; plan->rank = rank; plan->n = n;
+  if (getenv("NBODY_LET_DEBUG")) {   // development aid: size of every rank's boundary tree and this rank's export counts
+    std::string line = "[let rank " + std::to_string(rank) + "] n=" + std::to_string(n) + " published:";
+    for (int q = 0; q < world; q++) {
+      int hdr[2] = {0, 0};
+      cudaMemcpy(hdr, m->peer_pub + (size_t)q * kPubBytes, 8, cudaMemcpyDeviceToHost);
+      line += " " + std::to_string(hdr[0]) + "/" + std::to_string(hdr[1]);
+    }
+    line += " export:";
+    for (int q = 0; q < world; q++) line += " " + std::to_string(all[(size_t)rank * msg + world + 1 + q]);
+    fprintf(stderr, "%s\n", line.c_str());
+  }
   // cap_let is the same on every rank (it derives from the body capacity), so an overflow anywhere fails everywhere
   for (int q = 0; q < world; q++)
     for (int d = 0; d < world; d++)
@@ -1454,46 +1515,16 @@ int bh_let_import(BHState& local, BHState& let, Comm* comm, const BHParams& p, c
 
 const float4* bh_let_sources(BHState& local) { return impl_of(local)->let_sorted; }
 
-// Step phase (4), after the kick-drift: new splitters from equal-work samples (damped), then the planned migration.
-// posm / vel / ids = the step's sorted arrays (capacity cap): the leaving prefix and suffix are sent, the arriving
-// bodies land behind the current ones; *next describes where the bodies of the next step sit.
-int bh_let_finish(BHState& local, Comm* comm, const BHParams& p, const LetPlan& plan, float4* posm, float4* vel, float4* acc, int32_t* ids,
-                  BodySegs* next, int* n_next, int* n_received, cudaStream_t s, double* launches) {
+// Step phase (4), after the kick-drift: new splitters from equal-work samples (damped); they take effect when the bodies
+// are sent to their domains at the start of the next step.
+int bh_let_finish(BHState& local, Comm* comm, const BHParams& p, const LetPlan& plan, cudaStream_t s, double* launches) {
   Impl* m = impl_of(local);
-  const int world = plan.world, rank = plan.rank, n = plan.n;
-  // (a) splitters for the next step
+  const int world = plan.world, n = plan.n;
   let_sample_cost_kernel<<<1, kCostBins, 0, s>>>(m->sort.keys[m->sorted], n, m->bin_cost, m->samples + (size_t)world * kLetMsg);
   NB_TRY(comm->all_gather_bytes(m->samples + (size_t)world * kLetMsg, m->samples, (size_t)kLetMsg * 8, s));
   NB_TRY(launch_splitters(m, world, p.let_damping, s));
   NB_CUDA(cudaMemsetAsync(m->bin_cost, 0, kCostBins * sizeof(uint32_t), s));
   *launches += 2;
-  // (b) migration as planned before the walks
-  *next = BodySegs{0, n, 0};
-  *n_next = n;
-  *n_received = 0;
-  if (!plan.migrate) return 0;
-  size_t sb[kMaxWorld], so[kMaxWorld], rb[kMaxWorld], ro[kMaxWorld];
-  int64_t incoming = 0;
-  for (int q = 0; q < world; q++) {
-    sb[q] = q == rank ? 0 : (size_t)(plan.send_off[q + 1] - plan.send_off[q]);
-    so[q] = (size_t)plan.send_off[q];
-    rb[q] = (size_t)plan.mig_recv[q];
-    ro[q] = (size_t)n + (size_t)incoming;
-    incoming += plan.mig_recv[q];
-  }
-  auto exchange = [&](void* buf, size_t elem) -> int {
-    size_t a[kMaxWorld], b[kMaxWorld], c2[kMaxWorld], d[kMaxWorld];
-    for (int q = 0; q < world; q++) { a[q] = sb[q] * elem; b[q] = so[q] * elem; c2[q] = rb[q] * elem; d[q] = ro[q] * elem; }
-    return comm->all_to_all_v(buf, a, b, buf, c2, d, s);
-  };
-  NB_TRY(exchange(posm, 16));
-  NB_TRY(exchange(vel, 16));
-  NB_TRY(exchange(acc, 16));     // a read-back after this step shows the acceleration the body got in it (Particles[i].Acceleration)
-  NB_TRY(exchange(ids, 4));
-  const int stay = plan.send_off[rank + 1] - plan.send_off[rank];
-  *next = BodySegs{plan.send_off[rank], stay, n};
-  *n_next = stay + (int)incoming;
-  *n_received = (int)incoming;
   return 0;
 }
 

@@ -76,14 +76,13 @@ int bh_forces_from(BHState& src, BHState& tgt_tree, const BHParams& p, const flo
 class Comm;
 void bh_let_forget_domains(BHState& st);
 int bh_let_redistribute(BHState& st, Comm* comm, const BHParams& p, float4* posm_a, float4* vel_a, int32_t* ids_a, float4* posm_b,
-                        float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local,
+                        float4* vel_b, int32_t* ids_b, int n, int64_t cap, const uint32_t* box_global, int* n_local, int* n_stay,
                         cudaStream_t s, double* launches);
 int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* posm, int n, int64_t cap, LetPlan* plan, cudaStream_t s,
                 double* launches);
 int bh_let_import(BHState& local, BHState& let, Comm* comm, const BHParams& p, const LetPlan& plan, const uint32_t* box_global, int* n_let,
                   cudaStream_t s, double* launches);
-int bh_let_finish(BHState& local, Comm* comm, const BHParams& p, const LetPlan& plan, float4* posm, float4* vel, float4* acc, int32_t* ids,
-                  BodySegs* next, int* n_next, int* n_received, cudaStream_t s, double* launches);
+int bh_let_finish(BHState& local, Comm* comm, const BHParams& p, const LetPlan& plan, cudaStream_t s, double* launches);
 int bh_let_return(BHState& local, Comm* comm, const int32_t* ids, int n, int64_t n_per, const float* rec, int rec_words, float* out,
                   int n_slice, int64_t first, cudaStream_t s, double* launches);
 const float4* bh_let_sources(BHState& local);

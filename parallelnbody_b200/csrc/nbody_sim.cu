@@ -123,6 +123,7 @@ struct nbody_sim {
   BHState tree_let;   // multi-GPU LET mode: tree over the points received from the peers
   int n_let = 0;
   int n_migrated = 0;
+  bool drifted = false;   // domain split: the bodies moved since they were last sent to their domains
   BodySegs segs;      // domain split: where this rank's bodies sit in d_posm / d_vel / d_ids before the next build
 
   // timing of the last call
@@ -365,6 +366,20 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       };
       bp.sticky_root = true;
       lap("cube");
+      if (s->drifted) {
+        // bodies that crossed into another rank's key range move there BEFORE the tree is built: a rank that kept such
+        // strays for a step would have to describe a handful of bodies scattered through its neighbours' domains, and the
+        // neighbours would export everything around them (measured: 6x larger imports). The splitters were updated at the
+        // end of the last step (equal-work quantiles, damped).
+        int n_new = 0, n_stay = 0;
+        NB_TRY(bh_let_redistribute(s->tree, s->comm, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local,
+                                   std::min(std::min(s->cap_posm, s->cap_posm2), s->cap_acc), s->d_box, &n_new, &n_stay, s->stream, &launches));
+        s->n_migrated = n_new - n_stay;
+        s->n_local = n_new;
+        s->segs = BodySegs{0, n_new, 0};
+        s->drifted = false;
+        lap("migrate");
+      }
       if (s->n_local <= 0) { set_error("Barnes-Hut domain split: a rank holds no bodies"); return NBODY_ERR_STATE; }
       NB_TRY(bh_build(s->tree, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local, s->d_box,
                       s->stream, &launches, &s->segs));
@@ -418,13 +433,9 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       }
       if (ev) NB_CUDA(cudaEventRecord(ev[3], s->stream));
       if (integrate) {
-        // bodies that left this rank's key range move on AFTER the step (they were its targets in this step), the arrivals
-        // are appended; a pure force evaluation (CreateOctree) leaves everything where it is
-        int n_next = (int)s->n_local, n_recv = 0;
-        NB_TRY(bh_let_finish(s->tree, s->comm, bp, plan, s->d_posm, s->d_vel, s->d_acc, s->d_ids, &s->segs, &n_next, &n_recv, s->stream, &launches));
-        s->n_local = n_next;
-        s->n_migrated = n_recv;
-        lap("migrate");
+        // the walks recorded their work along the sorted bodies: new splitters (equal-work quantiles, damped) for the next step
+        NB_TRY(bh_let_finish(s->tree, s->comm, bp, plan, s->stream, &launches));
+        s->drifted = true;
       }
       s->launches += launches;
       if (ev) NB_CUDA(cudaEventRecord(ev[4], s->stream));
@@ -525,9 +536,10 @@ int finish_set(nbody_sim* s) {
     BHParams bp;
     bp.sticky_root = true;
     double launches = 0;
-    int n_new = 0;
+    int n_new = 0, n_stay = 0;
     NB_TRY(bh_let_redistribute(s->tree, s->comm, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local,
-                               std::min(std::min(s->cap_posm, s->cap_posm2), s->cap_acc), s->d_box, &n_new, s->stream, &launches));
+                               std::min(std::min(s->cap_posm, s->cap_posm2), s->cap_acc), s->d_box, &n_new, &n_stay, s->stream, &launches));
+    s->drifted = false;
     s->launches += launches;
     s->n_local = n_new;
     s->segs = BodySegs{0, n_new, 0};
