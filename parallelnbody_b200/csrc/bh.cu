@@ -85,6 +85,8 @@ struct Impl {
   int* let_cnt = nullptr;          // [world] export counts (the tail of the send_off message, not an allocation of its own)
   uint32_t* bin_cost = nullptr;    // [kCostBins] interactions evaluated for the bodies of each equal-count bin (last step)
   bool splitters_valid = false;    // the splitters describe balanced domains of the system this handle last ran
+  int* h_counts = nullptr;         // pinned host copy of the gathered per-step count message
+  cudaEvent_t ev_counts = nullptr; // fires when h_counts is filled
   float* ret = nullptr;            // read-back staging (return to owner)
   int64_t cap_ret = 0;
   int64_t cap_let = 0;
@@ -741,7 +743,6 @@ int launch_walk(Impl* m, Impl* g, const BHParams& p, const float4* posm, const f
                 bool accumulate, cudaStream_t s) {
   int per_sm = 0;
   NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<B, EPS0>, kWalkThreads, 0));
-  if (p.leave_sm_slot) per_sm -= 1;   // room for a concurrent stream's kernels (LET exchange overlapped with this walk)
   const int grid = sm_count() * std::max(1, std::min(per_sm, 8));
   const int64_t need = (int64_t)grid * kWalkWarps * kStackCap;
   if (need > m->cap_stacks) {
@@ -777,7 +778,7 @@ void bh_free(BHState& st) {
   cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->groups); cudaFree(m->group_cost);
   cudaFree(m->counters); cudaFree(m->root); cudaFree(m->stacks); cudaFree(m->boxes);
   cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_pub); cudaFree(m->pub_node);
-  cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->bin_cost); cudaFree(m->ret); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);
+  cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->bin_cost); cudaFree(m->ret); if (m->h_counts) cudaFreeHost(m->h_counts); if (m->ev_counts) cudaEventDestroy(m->ev_counts); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);
   delete m;
   st.impl = nullptr;
 }
@@ -827,7 +828,7 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
       NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split_ctas, tree_split_kernel, 256, 0));
       split_ctas = std::max(1, std::min(split_ctas, 8));
     }
-    NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(sm_count() * (p.leave_sm_slot ? 1 : split_ctas)), dim3(256), args, 0, s));
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(sm_count() * split_ctas), dim3(256), args, 0, s));
   }
   monopole_kernel<<<sm_count() * 8, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
   *launches += 2;
@@ -920,21 +921,21 @@ int bh_leaf_boxes(BHState& st, const float4* posm, int n, float* boxes7, int64_t
 // step to step). splitters[r] = first key of rank r's domain.
 //   when the bodies are set (bh_let_redistribute, eager): keys -> regular samples -> all-gather -> splitters (kept ones
 //       are reused when the caller sets the bodies again) -> bodies bucketed by destination and exchanged.
-//   per step, ONE host synchronisation:
-//     (1) local sort + tree over the bodies held now (bh_build);
-//     (2) bh_let_plan: where the sorted bodies would go under the current splitters (a prefix leaves to lower ranks, a
-//         suffix to higher ranks: lower bounds of the splitters in the sorted keys); the rank's domain boxes (a cut of
-//         its tree) are all-gathered; the local tree is descended for all peers at once with the reference's acceptance
-//         rule taken against the NEAREST box of each peer (so it holds for every body of the peer): accepted cells are
-//         exported as point masses, opened leaves as bodies; export counts and migration counts travel in one all-gather,
-//         which the host reads (the one synchronisation);
-//     (3) bh_let_import: export lists exchanged (all-to-all-v), the received points get their own tree; meanwhile the
-//         local walk runs on the main stream; then the walk over the received points;
-//     (4) bh_let_finish, after the kick-drift: new splitters = equal-WORK quantiles (the walks add each group's
+//   per step:
+//     (1) bodies that drifted out of the rank's key range are sent to their new owners (bh_let_redistribute again: one
+//         bucket pass by destination + all-to-all-v; one host read for the counts), so no rank ever holds strays inside a
+//         neighbour's domain - a few scattered strays would make the neighbours export everything around them;
+//     (2) local sort + tree (bh_build);
+//     (3) bh_let_plan: the rank publishes its BOUNDARY TREE (every cell whose parent holds more than n / 1024 bodies, with
+//         the bounding box of its bodies; all-gathered); the local tree is descended for all peers at once with the
+//         reference's acceptance rule taken against the peer's boundary tree (a published cell whose box is far enough
+//         settles all its bodies, a published leaf that is too close opens the cell): accepted cells are exported as
+//         point masses, opened leaves as bodies; the export counts are all-gathered and copied to pinned host memory;
+//     (4) the local walk is enqueued; the host waits only for the counts (bh_let_plan_wait), then enqueues the exchange
+//         of the export lists (bh_let_import, all-to-all-v), the tree over the received points and the walk through it;
+//     (5) bh_let_finish, after the kick-drift: new splitters = equal-WORK quantiles (the walks add each group's
 //         interaction count into 1024 bins along the sorted bodies; every rank contributes 256 equal-work samples),
-//         damped by one half; then the bodies that left the rank's key range are sent to their new owners and the
-//         received ones appended - LAZILY: they were still this rank's targets in this step. Ownership only affects
-//         balance, never results: a rank's boxes always cover the bodies it actually holds.
+//         damped by one half; they take effect in (1) of the next step.
 // The reference has no counterpart (it is single threaded); forces equal the single-GPU walk up to the (stricter)
 // acceptance of remote cells and summation order.
 // =====================================================================================================================
@@ -1303,6 +1304,9 @@ int let_ensure(Impl* m, int world, int64_t cap_local, cudaStream_t s) {
     NB_TRY(realloc_dev(&m->peer_pub, (size_t)world * kPubBytes));
     NB_TRY(realloc_dev(&m->pub_node, (size_t)kLetPub));
     NB_TRY(realloc_dev(&m->bin_cost, (size_t)kCostBins));
+    if (m->h_counts) NB_CUDA(cudaFreeHost(m->h_counts));
+    NB_CUDA(cudaHostAlloc((void**)&m->h_counts, (size_t)world * (2 * world + 2) * sizeof(int), cudaHostAllocDefault));
+    if (!m->ev_counts) NB_CUDA(cudaEventCreateWithFlags(&m->ev_counts, cudaEventDisableTiming));
     NB_CUDA(cudaMemsetAsync(m->bin_cost, 0, kCostBins * sizeof(uint32_t), s));
     m->let_cnt = m->send_off + world + 1;      // the per-step count message: [world + 1] send_off | [world] export counts
     m->let_world = world;
@@ -1434,15 +1438,25 @@ int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* pos
   // one message per rank: [world + 1] migration offsets | [world] export counts; one all-gather, one host read
   const int msg = 2 * world + 1;
   NB_TRY(comm->all_gather_bytes(m->send_off, m->all_off, (size_t)msg * 4, s));
-  std::vector<int> all((size_t)world * msg);
-  NB_CUDA(cudaMemcpyAsync(all.data(), m->all_off, all.size() * 4, cudaMemcpyDeviceToHost, s));
-  NB_CUDA(cudaStreamSynchronize(s));
+  NB_CUDA(cudaMemcpyAsync(m->h_counts, m->all_off, (size_t)world * msg * 4, cudaMemcpyDeviceToHost, s));   // pinned: truly asynchronous
+  NB_CUDA(cudaEventRecord(m->ev_counts, s));
   plan->world = world; plan->rank = rank; plan->n = n;
+  return 0;
+}
+
+// Second half of the plan: wait for the counts only (work enqueued on the stream after bh_let_plan - the local walk - keeps
+// running), then fill the host-side plan.
+int bh_let_plan_wait(BHState& local, int64_t cap, LetPlan* plan) {
+  Impl* m = impl_of(local);
+  const int world = plan->world, rank = plan->rank;
+  const int msg = 2 * world + 1;
+  NB_CUDA(cudaEventSynchronize(m->ev_counts));
+  const int* all = m->h_counts;
   if (getenv("NBODY_LET_DEBUG")) {   // development aid: size of every rank's boundary tree and this rank's export counts
-    std::string line = "[let rank " + std::to_string(rank) + "] n=" + std::to_string(n) + " published:";
+    std::string line = "[let rank " + std::to_string(rank) + "] n=" + std::to_string(plan->n) + " published:";
     for (int q = 0; q < world; q++) {
       int hdr[2] = {0, 0};
-      cudaMemcpy(hdr, m->peer_pub + (size_t)q * kPubBytes, 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(hdr, m->peer_pub + (size_t)q * kPubBytes, 8, cudaMemcpyDeviceToHost);   // (waits for the whole device)
       line += " " + std::to_string(hdr[0]) + "/" + std::to_string(hdr[1]);
     }
     line += " export:";
@@ -1457,25 +1471,13 @@ int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* pos
         return -5;
       }
   int64_t let_total = 0;
-  bool fits = true;
   for (int q = 0; q < world; q++) {
-    const int* theirs = all.data() + (size_t)q * msg;
-    plan->send_off[q] = all[(size_t)rank * msg + q];
-    plan->mig_recv[q] = q == rank ? 0 : theirs[rank + 1] - theirs[rank];
     plan->let_send[q] = all[(size_t)rank * msg + world + 1 + q];
-    plan->let_recv[q] = theirs[world + 1 + rank];
+    plan->let_recv[q] = all[(size_t)q * msg + world + 1 + rank];
     let_total += plan->let_recv[q];
   }
-  plan->send_off[world] = all[(size_t)rank * msg + world];
-  // lazy migration is taken only when it fits on EVERY rank (all ranks evaluate the same numbers: same decision)
-  for (int d = 0; d < world; d++) {
-    int64_t incoming = 0;
-    for (int q = 0; q < world; q++) if (q != d) incoming += all[(size_t)q * msg + d + 1] - all[(size_t)q * msg + d];
-    const int64_t n_d = all[(size_t)d * msg + world];
-    if (n_d + incoming > cap) fits = false;
-  }
-  plan->migrate = fits;
   plan->let_total = let_total;
+  (void)cap;
   return 0;
 }
 

@@ -23,7 +23,6 @@ struct BHParams {
   bool reference_root = false;
   int mac = kMacGroup;
   int group_size = 32;  // bodies per walk group: 32, 64 or 128 (1, 2 or 4 per lane)
-  bool leave_sm_slot = false;  // walk with one CTA per SM fewer than fit, so kernels of another stream can run beside it
   int depth_hint = 0;          // last known tree depth (0 = unknown): how many key levels the sort has to resolve
   int group_pack = 2;   // cells of <= group_pack * group_size bodies are cut into equal walk groups
   bool sticky_root = false;    // keep the previous root cube while it holds all bodies (multi-GPU domain split: keys stay comparable)
@@ -40,10 +39,7 @@ struct BodySegs {
 // What one step of the domain-split mode exchanges, known on the host after the step's one synchronisation.
 struct LetPlan {
   int world = 1, rank = 0, n = 0;
-  int send_off[17] = {0};      // sorted bodies [send_off[q], send_off[q + 1]) belong to rank q under the current splitters
-  int mig_recv[16] = {0};      // bodies arriving from rank q
   int let_send[16] = {0}, let_recv[16] = {0};   // locally-essential points to / from rank q
-  bool migrate = false;        // the migration fits the buffers of every rank
   int64_t let_total = 0;
 };
 
@@ -80,6 +76,7 @@ int bh_let_redistribute(BHState& st, Comm* comm, const BHParams& p, float4* posm
                         cudaStream_t s, double* launches);
 int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* posm, int n, int64_t cap, LetPlan* plan, cudaStream_t s,
                 double* launches);
+int bh_let_plan_wait(BHState& local, int64_t cap, LetPlan* plan);
 int bh_let_import(BHState& local, BHState& let, Comm* comm, const BHParams& p, const LetPlan& plan, const uint32_t* box_global, int* n_let,
                   cudaStream_t s, double* launches);
 int bh_let_finish(BHState& local, Comm* comm, const BHParams& p, const LetPlan& plan, cudaStream_t s, double* launches);

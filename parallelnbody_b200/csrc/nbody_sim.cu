@@ -91,10 +91,6 @@ struct nbody_sim {
 
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaStream_t stream_x = nullptr;          // LET mode: exchange stream, runs beside the local walk
-  cudaEvent_t ev_built = nullptr, ev_let = nullptr;
-  cudaEvent_t ev_walk[4] = {nullptr, nullptr, nullptr, nullptr};   // LET mode: around the local walk and the LET walk
-  bool walk_timed = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_pool;
 
@@ -358,7 +354,6 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       auto lap = [&](const char* what) {
         if (!trace) return;
         cudaStreamSynchronize(s->stream);
-        if (s->stream_x) cudaStreamSynchronize(s->stream_x);
         const auto now = std::chrono::steady_clock::now();
         fprintf(stderr, "[let rank %d step %lld] %-14s %8.3f ms  n_local=%lld n_let=%d\n", s->cfg.rank, (long long)s->steps, what,
                 std::chrono::duration<double, std::milli>(now - t_prev).count(), (long long)s->n_local, s->n_let);
@@ -390,37 +385,18 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       s->ids_identity = false;
       lap("local build");
       if (ev) { NB_CUDA(cudaEventRecord(ev[1], s->stream)); NB_CUDA(cudaEventRecord(ev[5], s->stream)); }
-      // The local walk (stream) and the plan + LET exchange + LET tree build (stream_x, incl. the host synchronisation for
-      // the counts) are independent: run them side by side; the walk of the received points waits for both.
-      if (!s->stream_x) {
-        int lo = 0, hi = 0;
-        NB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        NB_CUDA(cudaStreamCreateWithPriority(&s->stream_x, cudaStreamNonBlocking, hi));
-        NB_CUDA(cudaEventCreateWithFlags(&s->ev_built, cudaEventDisableTiming));
-        NB_CUDA(cudaEventCreateWithFlags(&s->ev_let, cudaEventDisableTiming));
-      }
-      const bool overlap = !trace && getenv("NBODY_LET_NO_OVERLAP") == nullptr;
-      cudaStream_t sx = overlap ? s->stream_x : s->stream;
+      // One stream, full occupancy: publish + export + count exchange, then the local walk; the host waits only for the
+      // counts (they sit in front of the walk), and enqueues the exchange of the export lists, the tree over the received
+      // points and the walk through it behind the local walk.
       LetPlan plan;
       const int64_t cap = std::min(std::min(s->cap_posm, s->cap_posm2), s->cap_acc);
-      if (overlap) {
-        NB_CUDA(cudaEventRecord(s->ev_built, s->stream));
-        NB_CUDA(cudaStreamWaitEvent(sx, s->ev_built, 0));
-        bp.leave_sm_slot = true;
-        NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
-      }
-      NB_TRY(bh_let_plan(s->tree, s->comm, bp, s->d_posm, (int)s->n_local, cap, &plan, sx, &launches));
+      NB_TRY(bh_let_plan(s->tree, s->comm, bp, s->d_posm, (int)s->n_local, cap, &plan, s->stream, &launches));
       lap("plan + export");
-      NB_TRY(bh_let_import(s->tree, s->tree_let, s->comm, bp, plan, s->d_box, &s->n_let, sx, &launches));
+      NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
+      NB_TRY(bh_let_plan_wait(s->tree, cap, &plan));
+      lap("walk local");
+      NB_TRY(bh_let_import(s->tree, s->tree_let, s->comm, bp, plan, s->d_box, &s->n_let, s->stream, &launches));
       lap("let import");
-      if (overlap) {
-        NB_CUDA(cudaEventRecord(s->ev_let, sx));
-        NB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_let, 0));
-      } else {
-        NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
-        lap("walk local");
-      }
-      bp.leave_sm_slot = false;
       if (s->n_let > 0)
         NB_TRY(bh_forces_from(s->tree_let, s->tree, bp, bh_let_sources(s->tree), s->d_posm, s->d_acc, s->n_let, 0, (int)s->n_local,
                               true, s->stream, &launches));
@@ -718,10 +694,6 @@ void nbody_destroy(nbody_sim* s) {
   for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
-  if (s->stream_x) cudaStreamDestroy(s->stream_x);
-  for (cudaEvent_t e : s->ev_walk) if (e) cudaEventDestroy(e);
-  if (s->ev_built) cudaEventDestroy(s->ev_built);
-  if (s->ev_let) cudaEventDestroy(s->ev_let);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
