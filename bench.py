@@ -44,6 +44,7 @@ WORKLOADS = {
     "plummer_1m_bh": ("plummer", 1 << 20, "bh", 0.01, 0.25, 1e-3),            # BASELINE configs[3]: theta_conv = 0.5
     "two_galaxies_16m_bh": ("two_galaxies", 1 << 24, "bh", 0.01, 0.35, 1e-3),  # BASELINE configs[4]: theta_conv = 0.7
     "two_galaxies_2m_bh": ("two_galaxies", 1 << 21, "bh", 0.01, 0.35, 1e-3),
+    "two_galaxies_4m_bh": ("two_galaxies", 1 << 22, "bh", 0.01, 0.35, 1e-3),
 }
 
 
@@ -308,6 +309,8 @@ def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_basel
     barrier()
     wall0 = time.perf_counter()
     ms = {"total": 0.0, "force": 0.0, "build": 0.0, "integrate": 0.0, "comm": 0.0}
+    LET_KEYS = ("ms_let_migrate", "ms_let_plan", "ms_let_walk_local", "ms_let_import", "ms_let_walk_let")
+    let_ms = {k: 0.0 for k in LET_KEYS}
     interactions = 0.0
     for _ in range(steps):
         flush_l2()
@@ -316,6 +319,8 @@ def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_basel
         ms["total"] += st["ms_last_call"]; ms["force"] += st["ms_force"]; ms["build"] += st["ms_build"]
         ms["integrate"] += st["ms_integrate"]; ms["comm"] += st["ms_comm"]
         interactions += st["interactions"]
+        for k in LET_KEYS:
+            let_ms[k] += st[k]
     barrier()
     wall = time.perf_counter() - wall0
     clk = clocks.stop() if rank == 0 else None
@@ -326,6 +331,8 @@ def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_basel
     phase_max = {k: max_over_ranks(v) / steps for k, v in ms.items() if k != "total"}
     n_local_max, n_local_min = max_over_ranks(float(st["n_local"])), -max_over_ranks(-float(st["n_local"]))
     let_max = max_over_ranks(float(st["let_points"]))
+    let_phases = {k[7:]: max_over_ranks(let_ms[k] / steps) for k in LET_KEYS}
+    let_phases_min = {k[7:]: -max_over_ranks(-let_ms[k] / steps) for k in LET_KEYS}
 
     # ---- end to end through the public API with HOST buffers (pinned FParticle arrays in, Tick, FParticle arrays out)
     aos_in = torch.empty(n * 40, dtype=torch.uint8).pin_memory()
@@ -404,6 +411,10 @@ def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_basel
     if method == "bh":
         res["bodies_per_rank"] = {"min": n_local_min, "max": n_local_max}
         res["let_points_max"] = let_max
+        if lets:
+            res["domain_split_phases_ms_per_step_max_over_ranks"] = let_phases
+            res["domain_split_phases_ms_per_step_min_over_ranks"] = let_phases_min
+            res["longest_phase"] = "domain split: " + max(let_phases, key=let_phases.get)
         res["tree"] = {"nodes": stats["tree_nodes"], "depth": stats["tree_depth"], "walk_groups": stats["walk_groups"]}
     if with_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(wl, posm, vel)

@@ -111,7 +111,10 @@ typedef struct nbody_stats {
   int32_t equal_mass;      /* direct sum: 1 = all sources carry one mass, the 11-lane-op kernel runs (mass applied in K2) */
   int32_t sort_passes;     /* BH: 8-bit radix passes of the last build (only the key levels the tree needs are sorted) */
   int32_t migrated;        /* BH domain split: bodies this rank received from other ranks in the last step */
-  int32_t reserved[5];
+  /* BH domain split, last step of the last synchronous call, device time (ms): sending bodies to their domains; boundary
+   * tree + export descent + count exchange; local walk; exchange of the export lists + tree over the received points;
+   * walk through the received points */
+  float ms_let_migrate, ms_let_plan, ms_let_walk_local, ms_let_import, ms_let_walk_let;
 } nbody_stats;
 
 typedef struct nbody_sim nbody_sim; /* opaque handle: owns device buffers, stream, events, NCCL communicator */

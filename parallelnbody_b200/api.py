@@ -49,7 +49,9 @@ class Stats(C.Structure):
                 ("ms_integrate", C.c_float), ("ms_comm", C.c_float), ("cube_size", C.c_float), ("jsplit", C.c_int32),
                 ("i_per_thread", C.c_int32), ("tree_nodes", C.c_int32), ("tree_depth", C.c_int32),
                 ("root_com", C.c_float * 3), ("root_mass", C.c_float), ("walk_groups", C.c_int32), ("let_points", C.c_int32),
-                ("equal_mass", C.c_int32), ("sort_passes", C.c_int32), ("migrated", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("equal_mass", C.c_int32), ("sort_passes", C.c_int32), ("migrated", C.c_int32),
+                ("ms_let_migrate", C.c_float), ("ms_let_plan", C.c_float), ("ms_let_walk_local", C.c_float), ("ms_let_import", C.c_float),
+                ("ms_let_walk_let", C.c_float)]
 
     def as_dict(self):
         d = {}

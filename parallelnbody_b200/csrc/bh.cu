@@ -62,6 +62,9 @@ struct Impl {
   int4* node_meta = nullptr;
   int2* node_range = nullptr;
   uint32_t* node_ready = nullptr;
+  float4* node_bmin = nullptr;       // bounding box of every node's bodies (domain-split mode only)
+  float4* node_bmax = nullptr;
+  int64_t cap_boxes_nodes = 0;
   int2* groups = nullptr;            // walk groups: body ranges of <= group_size neighbours
   int* group_cost = nullptr;         // interaction-list length of each group in the last walk (work measure for the domain split)
   Counters* counters = nullptr;
@@ -380,10 +383,13 @@ tree_split_kernel(const uint64_t* __restrict__ keys, const int leaf_size, const 
 // Leaves sum their bodies; the last child to arrive at a parent sums the parent's children in octant order:
 //   TotalMass += Mc;  CenterOfMass += COMc * Mc;  CenterOfMass *= 1 / TotalMass   (fp32, as the reference; M == 0 keeps
 // a position inside the cell, h:95), with the first-order sums taken about the first child.
+template <bool BOXES>
 __global__ void __launch_bounds__(256)
 monopole_kernel(const float4* __restrict__ posm, const int2* __restrict__ range, const int4* __restrict__ meta,
                 uint32_t* __restrict__ ready, float4* __restrict__ com, const Counters* __restrict__ c,
-                float4* __restrict__ root) {
+                float4* __restrict__ root, float4* __restrict__ bmin, float4* __restrict__ bmax) {
+  // BOXES: also the bounding box of every node's bodies (bmin / bmax), carried up the same way - the domain-split mode
+  // describes a rank's domain to its peers with them
   const int nn = c->nnodes;
   for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < nn; node += gridDim.x * blockDim.x) {
     int4 m = meta[node];
@@ -392,13 +398,16 @@ monopole_kernel(const float4* __restrict__ posm, const int2* __restrict__ range,
     // body never sees its own cell's monopole at a rounding-error distance)
     const float4 p0 = posm[m.x];
     float M = 0.f, x = 0.f, y = 0.f, z = 0.f;
+    float lx = p0.x, ly = p0.y, lz = p0.z, hx = p0.x, hy = p0.y, hz = p0.z;
     for (int b = m.x; b < m.x + m.y; b++) {
       const float4 p = posm[b];
       M += p.w; x += (p.x - p0.x) * p.w; y += (p.y - p0.y) * p.w; z += (p.z - p0.z) * p.w;
+      if (BOXES) { lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z); hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z); }
     }
     if (M != 0.f) { const float rv = 1.f / M; x = p0.x + x * rv; y = p0.y + y * rv; z = p0.z + z * rv; }
     else { x = p0.x; y = p0.y; z = p0.z; }
     __stcg(com + node, make_float4(x, y, z, M));
+    if (BOXES) { __stcg(bmin + node, make_float4(lx, ly, lz, 0.f)); __stcg(bmax + node, make_float4(hx, hy, hz, 0.f)); }
     while (true) {
       const int parent = m.w;
       if (parent < 0) { root[1] = make_float4(x, y, z, 1.f); break; }   // next reference-mode root centre (OctreeSearch.cpp:77)
@@ -411,10 +420,16 @@ monopole_kernel(const float4* __restrict__ posm, const int2* __restrict__ range,
       for (int k = 0; k < m.y; k++) {
         const float4 q = __ldcg(com + m.x + k);
         M += q.w; x += (q.x - q0.x) * q.w; y += (q.y - q0.y) * q.w; z += (q.z - q0.z) * q.w;
+        if (BOXES) {
+          const float4 a = __ldcg(bmin + m.x + k), b = __ldcg(bmax + m.x + k);
+          if (k == 0) { lx = a.x; ly = a.y; lz = a.z; hx = b.x; hy = b.y; hz = b.z; }
+          else { lx = fminf(lx, a.x); ly = fminf(ly, a.y); lz = fminf(lz, a.z); hx = fmaxf(hx, b.x); hy = fmaxf(hy, b.y); hz = fmaxf(hz, b.z); }
+        }
       }
       if (M != 0.f) { const float rv = 1.f / M; x = q0.x + x * rv; y = q0.y + y * rv; z = q0.z + z * rv; }
       else { x = q0.x; y = q0.y; z = q0.z; }
       __stcg(com + parent, make_float4(x, y, z, M));
+      if (BOXES) { __stcg(bmin + parent, make_float4(lx, ly, lz, 0.f)); __stcg(bmax + parent, make_float4(hx, hy, hz, 0.f)); }
     }
   }
 }
@@ -775,7 +790,7 @@ void bh_free(BHState& st) {
   Impl* m = static_cast<Impl*>(st.impl);
   for (int k = 0; k < 2; k++) { cudaFree(m->sort.keys[k]); cudaFree(m->sort.idx[k]); }
   cudaFree(m->sort.work);
-  cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->groups); cudaFree(m->group_cost);
+  cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->node_bmin); cudaFree(m->node_bmax); cudaFree(m->groups); cudaFree(m->group_cost);
   cudaFree(m->counters); cudaFree(m->root); cudaFree(m->stacks); cudaFree(m->boxes);
   cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_pub); cudaFree(m->pub_node);
   cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->bin_cost); cudaFree(m->ret); if (m->h_counts) cudaFreeHost(m->h_counts); if (m->ev_counts) cudaEventDestroy(m->ev_counts); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);
@@ -830,7 +845,17 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
     }
     NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(sm_count() * split_ctas), dim3(256), args, 0, s));
   }
-  monopole_kernel<<<sm_count() * 8, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root);
+  if (p.node_boxes) {
+    if (m->cap_boxes_nodes < m->cap_nodes) {
+      NB_CUDA(cudaStreamSynchronize(s));
+      NB_TRY(realloc_dev(&m->node_bmin, (size_t)m->cap_nodes));
+      NB_TRY(realloc_dev(&m->node_bmax, (size_t)m->cap_nodes));
+      m->cap_boxes_nodes = m->cap_nodes;
+    }
+    monopole_kernel<true><<<sm_count() * 8, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root, m->node_bmin, m->node_bmax);
+  } else {
+    monopole_kernel<false><<<sm_count() * 8, 256, 0, s>>>(posm, m->node_range, m->node_meta, m->node_ready, m->node_com, m->counters, m->root, nullptr, nullptr);
+  }
   *launches += 2;
   NB_CUDA(cudaGetLastError());
   return 0;
@@ -1084,109 +1109,71 @@ __global__ void let_offsets_kernel(const uint64_t* __restrict__ sorted, const in
   send_off[r] = lo;
 }
 
-// A rank describes its domain to its peers by the TOP OF ITS TREE ("boundary tree"): every cell whose parent holds more
-// than T bodies, with the bounding box of its bodies. Tree cells are spatially compact (a Morton range is not: it can jump
-// across the whole cube) and the description refines where the bodies are dense. Layout of the message (kPubBytes per rank):
-//   int header[32]: [0] = number of published cells, [1] = number of levels, [2 + l] = first cell of level l
+// A rank describes its domain to its peers by the TOP OF ITS TREE ("boundary tree") with the bounding box of every
+// published cell's bodies. Tree cells are spatially compact (a Morton range is not: it can jump across the whole cube).
+// Layout of the message (kPubBytes per rank):
+//   int header[32]: [0] = number of published cells
 //   int2 child[kLetPub]: (first published child, number of children), (0, 0) for the leaves of the published tree
 //   float box[kLetPub][6]: min xyz, max xyz of the cell's bodies
 constexpr int kLetPub = 8192;
-constexpr int kPubLevels = 28;
 constexpr size_t kPubBytes = 32 * 4 + (size_t)kLetPub * 8 + (size_t)kLetPub * 24;
 __host__ __device__ inline const int* pub_header(const void* msg) { return reinterpret_cast<const int*>(msg); }
 __host__ __device__ inline const int2* pub_child(const void* msg) { return reinterpret_cast<const int2*>(reinterpret_cast<const char*>(msg) + 128); }
 __host__ __device__ inline const float* pub_box(const void* msg) { return reinterpret_cast<const float*>(reinterpret_cast<const char*>(msg) + 128 + (size_t)kLetPub * 8); }
 
-// One CTA: breadth-first from the root; a published cell with more than T bodies publishes its children (contiguous).
+// One CTA, rounds of refinement: in round r every published leaf that is an inner cell of the tree with more than
+// kPubMinBodies bodies and a bounding box wider than E_r = root width / 2^(r + 3) publishes its children (contiguous), as
+// long as they fit. What counts is the EXTENT of a published leaf, not its body count: a peer must open everything within
+// (cell size / theta) of the box, so a wide box around a few scattered bodies (the thin end of a Morton range) would make
+// the peer export a large part of its domain. Boxes come from the tree (monopole pass).
+constexpr int kPubMinBodies = 32;
 __global__ void __launch_bounds__(1024)
-let_publish_kernel(const int4* __restrict__ meta, const int2* __restrict__ range, const int n, const int T, int* __restrict__ pub_node,
+let_publish_kernel(const int4* __restrict__ meta, const int2* __restrict__ range, const float4* __restrict__ bmin,
+                   const float4* __restrict__ bmax, const float4* __restrict__ root, const int n, int* __restrict__ pub_node,
                    void* __restrict__ msg) {
   int* header = reinterpret_cast<int*>(msg);
   int2* child = reinterpret_cast<int2*>(reinterpret_cast<char*>(msg) + 128);
-  __shared__ int s_count, s_valid;
-  if (threadIdx.x == 0) { s_count = n > 0 ? 1 : 0; s_valid = s_count; pub_node[0] = 0; header[2] = 0; }
-  __syncthreads();
-  int lb = 0, le = s_valid, level = 0;     // cells of `level` = [lb, le)
-  while (lb < le) {
-    const bool last = level + 1 == kPubLevels;
-    for (int i = lb + threadIdx.x; i < le; i += blockDim.x) {
-      const int node = pub_node[i];
-      const int4 m = meta[node];
-      const int2 r = range[node];
-      int2 ch = make_int2(0, 0);
-      if (!last && !(m.z & kLeafFlag) && r.y - r.x > T) {
-        const int slot = atomicAdd(&s_count, m.y);
-        if (slot + m.y <= kLetPub) {      // allocations are handed out in order: the ones that fit form a contiguous prefix
-          ch = make_int2(slot, m.y);
-          for (int k = 0; k < m.y; k++) pub_node[slot + k] = m.x + k;
-          atomicMax(&s_valid, slot + m.y);
-        }
-      }
-      child[i] = ch;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) header[2 + level + 1] = le;
-    lb = le;
-    le = s_valid;
-    level++;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { header[0] = lb; header[1] = level; }
-}
-
-// One CTA per published cell: the leaves of the published tree get the bounding box of their bodies, the inner cells an
-// empty box (filled bottom-up by let_pub_union_kernel).
-__global__ void __launch_bounds__(256)
-let_pub_boxes_kernel(const float4* __restrict__ posm, const int2* __restrict__ range, const int* __restrict__ pub_node, void* __restrict__ msg) {
-  const int b = blockIdx.x;
-  const int* header = reinterpret_cast<const int*>(msg);
-  if (b >= header[0]) return;
-  const int2 ch = reinterpret_cast<const int2*>(reinterpret_cast<const char*>(msg) + 128)[b];
-  float* box = reinterpret_cast<float*>(reinterpret_cast<char*>(msg) + 128 + (size_t)kLetPub * 8) + (size_t)b * 6;
-  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-  if (ch.y == 0) {
-    const int2 r = range[pub_node[b]];
-    for (int i = r.x + threadIdx.x; i < r.y; i += blockDim.x) {
-      const float4 p = posm[i];
-      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
-      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
-    }
-  }
-  __shared__ float s[8][6];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-    }
-  if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; k++) { s[threadIdx.x >> 5][k] = mn[k]; s[threadIdx.x >> 5][3 + k] = mx[k]; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 1; q < 8; q++) for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], s[q][k]); mx[k] = fmaxf(mx[k], s[q][3 + k]); }
-    for (int k = 0; k < 3; k++) { box[k] = mn[k]; box[3 + k] = mx[k]; }
-  }
-}
-
-// One CTA: inner cells = union of their children, level by level from the bottom.
-__global__ void __launch_bounds__(1024)
-let_pub_union_kernel(void* __restrict__ msg) {
-  const int* header = reinterpret_cast<const int*>(msg);
-  const int2* child = reinterpret_cast<const int2*>(reinterpret_cast<const char*>(msg) + 128);
   float* box = reinterpret_cast<float*>(reinterpret_cast<char*>(msg) + 128 + (size_t)kLetPub * 8);
-  const int levels = header[1];
-  for (int l = levels - 2; l >= 0; l--) {
-    const int lb = header[2 + l], le = header[2 + l + 1];
-    for (int i = lb + threadIdx.x; i < le; i += blockDim.x) {
-      const int2 ch = child[i];
-      if (ch.y == 0) continue;
-      float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-      for (int k = 0; k < ch.y; k++)
-        for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], box[(size_t)(ch.x + k) * 6 + a]); mx[a] = fmaxf(mx[a], box[(size_t)(ch.x + k) * 6 + 3 + a]); }
-      for (int a = 0; a < 3; a++) { box[(size_t)i * 6 + a] = mn[a]; box[(size_t)i * 6 + 3 + a] = mx[a]; }
-    }
-    __syncthreads();
+  __shared__ int s_count, s_valid, s_grew;
+  if (threadIdx.x == 0) {
+    s_count = n > 0 ? 1 : 0; s_valid = s_count; pub_node[0] = 0; child[0] = make_int2(0, 0);
+    if (n > 0) { const float4 a = bmin[0], b = bmax[0]; box[0] = a.x; box[1] = a.y; box[2] = a.z; box[3] = b.x; box[4] = b.y; box[5] = b.z; }
   }
+  __syncthreads();
+  float E = root[0].w * 0.25f;            // root width / 8
+  for (int round = 0; round < 14; round++, E *= 0.5f) {
+    // a round may need several sweeps: a cell published in this round can itself be wider than E
+    for (int sweep = 0; sweep < kMaxLevel + 1; sweep++) {
+      if (threadIdx.x == 0) s_grew = 0;
+      __syncthreads();
+      const int end = s_valid;
+      for (int i = threadIdx.x; i < end; i += blockDim.x) {
+        if (child[i].y != 0) continue;
+        const int node = pub_node[i];
+        const int4 m = meta[node];
+        const int2 r = range[node];
+        const float w = fmaxf(fmaxf(box[i * 6 + 3] - box[i * 6], box[i * 6 + 4] - box[i * 6 + 1]), box[i * 6 + 5] - box[i * 6 + 2]);
+        if ((m.z & kLeafFlag) || r.y - r.x <= kPubMinBodies || !(w > E)) continue;
+        const int slot = atomicAdd(&s_count, m.y);
+        if (slot + m.y > kLetPub) { atomicSub(&s_count, m.y); continue; }     // no room: stays a leaf of the published tree
+        for (int k = 0; k < m.y; k++) {
+          const int c = m.x + k, j = slot + k;
+          pub_node[j] = c;
+          child[j] = make_int2(0, 0);
+          const float4 a = bmin[c], b = bmax[c];
+          box[j * 6] = a.x; box[j * 6 + 1] = a.y; box[j * 6 + 2] = a.z; box[j * 6 + 3] = b.x; box[j * 6 + 4] = b.y; box[j * 6 + 5] = b.z;
+        }
+        child[i] = make_int2(slot, m.y);
+        atomicMax(&s_valid, slot + m.y);
+        s_grew = 1;
+      }
+      __syncthreads();
+      if (!s_grew) break;
+      __syncthreads();
+    }
+    if (s_valid > kLetPub - 8) break;
+  }
+  if (threadIdx.x == 0) { header[0] = s_valid; header[1] = 0; }
 }
 
 // Is the point mass (cm, cell half-width^2 / theta^2 = need) acceptable for EVERY body of a peer? Descends the peer's
@@ -1419,12 +1406,11 @@ int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* pos
     m->cap_visit = need_nodes;
   }
   NB_CUDA(cudaMemsetAsync(m->send_off, 0, (size_t)(world + 1) * 4, s));
-  // this rank's boundary tree: cells whose parent holds more than n / 1024 bodies, with their bounding boxes
+  // this rank's boundary tree: the top of its tree, refined until the published cells are small (or 8192 are used)
   char* my_pub = m->peer_pub + (size_t)rank * kPubBytes;
-  let_publish_kernel<<<1, 1024, 0, s>>>(m->node_meta, m->node_range, n, std::max(64, n / 1024), m->pub_node, my_pub);
-  let_pub_boxes_kernel<<<kLetPub, 256, 0, s>>>(posm, m->node_range, m->pub_node, my_pub);
-  let_pub_union_kernel<<<1, 1024, 0, s>>>(my_pub);
-  *launches += 3;
+  if (!m->node_bmin) { set_error("Barnes-Hut LET: the local tree was built without node boxes"); return -5; }
+  let_publish_kernel<<<1, 1024, 0, s>>>(m->node_meta, m->node_range, m->node_bmin, m->node_bmax, m->root, n, m->pub_node, my_pub);
+  *launches += 1;
   NB_TRY(comm->all_gather_bytes(my_pub, m->peer_pub, kPubBytes, s));
   NB_CUDA(cudaMemsetAsync(m->let_cnt, 0, (size_t)world * 4, s));
   if (n > 0) {
@@ -1505,6 +1491,7 @@ int bh_let_import(BHState& local, BHState& let, Comm* comm, const BHParams& p, c
   if (total > 0) {
     BHParams q = p;
     q.sticky_root = false;           // same cube as the local tree: copy it instead of deriving it again
+    q.node_boxes = false;
     Impl* l = impl_of(let);
     NB_TRY(ensure(l, (int)total, s));
     NB_CUDA(cudaMemcpyAsync(l->root, m->root, sizeof(float4), cudaMemcpyDeviceToDevice, s));

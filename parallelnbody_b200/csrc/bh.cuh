@@ -26,6 +26,7 @@ struct BHParams {
   int depth_hint = 0;          // last known tree depth (0 = unknown): how many key levels the sort has to resolve
   int group_pack = 2;   // cells of <= group_pack * group_size bodies are cut into equal walk groups
   bool sticky_root = false;    // keep the previous root cube while it holds all bodies (multi-GPU domain split: keys stay comparable)
+  bool node_boxes = false;     // the monopole pass also computes every node's bounding box (domain-split mode)
   bool keep_root = false;      // the root cube is already in place (tree over received points: same cube as the local tree)
   float let_damping = 0.5f;    // domain split: fraction of the way a splitter moves towards its new equal-work quantile per step
 };

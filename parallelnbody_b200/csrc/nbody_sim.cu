@@ -119,6 +119,8 @@ struct nbody_sim {
   BHState tree_let;   // multi-GPU LET mode: tree over the points received from the peers
   int n_let = 0;
   int n_migrated = 0;
+  cudaEvent_t ev_ph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // domain split: phase marks of the last step
+  float ms_ph[5] = {0, 0, 0, 0, 0};
   bool drifted = false;   // domain split: the bodies moved since they were last sent to their domains
   BodySegs segs;      // domain split: where this rank's bodies sit in d_posm / d_vel / d_ids before the next build
 
@@ -360,7 +362,11 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
         t_prev = now;
       };
       bp.sticky_root = true;
+      bp.node_boxes = true;
       lap("cube");
+      if (!s->ev_ph[0]) for (int q = 0; q < 8; q++) NB_CUDA(cudaEventCreate(&s->ev_ph[q]));
+      auto phase = [&](int k) { if (ev) cudaEventRecord(s->ev_ph[k], s->stream); };
+      phase(0);
       if (s->drifted) {
         // bodies that crossed into another rank's key range move there BEFORE the tree is built: a rank that kept such
         // strays for a step would have to describe a handful of bodies scattered through its neighbours' domains, and the
@@ -375,6 +381,7 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
         s->drifted = false;
         lap("migrate");
       }
+      phase(1);
       if (s->n_local <= 0) { set_error("Barnes-Hut domain split: a rank holds no bodies"); return NBODY_ERR_STATE; }
       NB_TRY(bh_build(s->tree, bp, s->d_posm, s->d_vel, s->d_ids, s->d_posm2, s->d_vel2, s->d_ids2, (int)s->n_local, s->d_box,
                       s->stream, &launches, &s->segs));
@@ -390,17 +397,22 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       // points and the walk through it behind the local walk.
       LetPlan plan;
       const int64_t cap = std::min(std::min(s->cap_posm, s->cap_posm2), s->cap_acc);
+      phase(2);
       NB_TRY(bh_let_plan(s->tree, s->comm, bp, s->d_posm, (int)s->n_local, cap, &plan, s->stream, &launches));
       lap("plan + export");
+      phase(3);
       NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
+      phase(4);
       NB_TRY(bh_let_plan_wait(s->tree, cap, &plan));
       lap("walk local");
       NB_TRY(bh_let_import(s->tree, s->tree_let, s->comm, bp, plan, s->d_box, &s->n_let, s->stream, &launches));
       lap("let import");
+      phase(5);
       if (s->n_let > 0)
         NB_TRY(bh_forces_from(s->tree_let, s->tree, bp, bh_let_sources(s->tree), s->d_posm, s->d_acc, s->n_let, 0, (int)s->n_local,
                               true, s->stream, &launches));
       lap("walk let");
+      phase(6);
       if (ev) NB_CUDA(cudaEventRecord(ev[2], s->stream));
       if (integrate) {
         kick_drift_kernel<<<(unsigned)ceil_div(s->n_local, 256), 256, 0, s->stream>>>((int)s->n_local, dt, s->d_posm, s->d_vel, s->d_acc);
@@ -476,6 +488,10 @@ int run_steps(nbody_sim* s, float dt, int nsteps, bool integrate, bool sync) {
   if (timed > 0 && timed < nsteps) {  // scale the sampled phases to the whole call
     const float f = (float)nsteps / (float)timed;
     s->ms_build *= f; s->ms_force *= f; s->ms_integrate *= f; s->ms_comm *= f;
+  }
+  if (s->let_mode() && timed > 0 && s->ev_ph[0]) {
+    const int a[5] = {0, 2, 3, 4, 5}, b[5] = {1, 3, 4, 5, 6};
+    for (int q = 0; q < 5; q++) if (cudaEventElapsedTime(&s->ms_ph[q], s->ev_ph[a[q]], s->ev_ph[b[q]]) != cudaSuccess) { s->ms_ph[q] = 0; cudaGetLastError(); }
   }
   if (s->cfg.method == NBODY_BARNES_HUT) {
     NB_TRY(bh_fetch_stats(s->tree, s->stream, &s->interactions));
@@ -692,6 +708,7 @@ void nbody_destroy(nbody_sim* s) {
   cudaFree(s->d_posm); cudaFree(s->d_vel); cudaFree(s->d_acc); cudaFree(s->d_partial); cudaFree(s->d_ids);
   cudaFree(s->d_stage); cudaFree(s->d_ret); cudaFree(s->d_acc2); cudaFree(s->d_box); cudaFree(s->d_energy);
   for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_ph) if (e) cudaEventDestroy(e);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -979,6 +996,8 @@ int nbody_stats_get(nbody_sim* s, nbody_stats* out) {
   out->equal_mass = s->equal_mass ? 1 : 0;
   out->sort_passes = s->tree.sort_passes_host;
   out->migrated = s->n_migrated;
+  out->ms_let_migrate = s->ms_ph[0]; out->ms_let_plan = s->ms_ph[1]; out->ms_let_walk_local = s->ms_ph[2]; out->ms_let_import = s->ms_ph[3];
+  out->ms_let_walk_let = s->ms_ph[4];
   memcpy(out->root_com, s->tree.root_com_host, sizeof(out->root_com));
   out->root_mass = s->tree.root_mass_host;
   return NBODY_OK;
