@@ -815,11 +815,11 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
     root_cube_kernel<<<1, 1, 0, s>>>(box, p.reference_root ? 1 : (p.sticky_root ? 2 : 0), m->root);
     *launches += 1;
   }
-  // Sort only as many levels as the tree needs: the last known depth + 4 (a cell at the last sorted level is a leaf
+  // Sort only as many levels as the tree needs: the last known depth + 2 (a cell at the last sorted level is a leaf
   // whatever it holds, so a too-small hint costs accuracy nothing, only walk efficiency, and corrects itself through
   // the depth statistic). The parity configurations (one-body leaves / per-body walk) always sort all 63 bits.
   int levels = kMaxLevel;
-  if (p.leaf_size > 1 && p.mac == kMacGroup && p.depth_hint > 0 && !getenv("NBODY_FULL_SORT")) levels = std::min(kMaxLevel, std::max(10, p.depth_hint + 4));
+  if (p.leaf_size > 1 && p.mac == kMacGroup && p.depth_hint > 0 && !getenv("NBODY_FULL_SORT")) levels = std::min(kMaxLevel, std::max(10, p.depth_hint + 2));
   const RadixPlan plan = radix_sort_begin(m->sort, n, 3 * kMaxLevel, s, 3 * (kMaxLevel - levels));
   const unsigned nbk = (unsigned)std::min<int64_t>(nb, (int64_t)sm_count() * 16);   // grid-stride: few histogram flushes per CTA
   morton_kernel<<<nbk, 256, 0, s>>>(posm_in, n, m->root, m->sort.keys[0], plan.ghist0, plan.shift0, segs);
