@@ -82,7 +82,7 @@ struct Impl {
   int* all_off = nullptr;          // [world * (2 world + 1)] every rank's message
   char* peer_pub = nullptr;        // [world * kPubBytes] every rank's published boundary tree (cells + bounding boxes)
   int* pub_node = nullptr;         // [kLetPub] local tree node behind each published cell
-  uint32_t* visit = nullptr;       // per node: which peers still descend through it
+  uint32_t* visit = nullptr;       // export descent: 2 x (cells, peer masks) frontiers of cap_visit entries + 2 counters
   int64_t cap_visit = 0;
   float4* let_out = nullptr;       // [world * cap_let] per-peer export lists
   int* let_cnt = nullptr;          // [world] export counts (the tail of the send_off message, not an allocation of its own)
@@ -1214,28 +1214,37 @@ __device__ __forceinline__ bool let_accept_for_peer(const float4 cm, const float
   return true;
 }
 
-// The export descent, all peers at once, all generations in one cooperative launch. visit[node] = bit mask of the
-// peers that reached this node (written by the parent one generation earlier).
+// The export descent, all peers at once, in one cooperative launch: a frontier of (cell, mask of the peers that still
+// descend through it) per generation, so the work is proportional to the cells actually visited. frontier = 2 x 2 x cap
+// words (cell, mask; current and next generation); fr_count[2] = their lengths (fr_count[0] = 1, frontier[0] = root before
+// the launch).
 __global__ void __launch_bounds__(256)
 let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com,
-                  const int4* __restrict__ node_meta, const Counters* __restrict__ c, const float4* __restrict__ root,
+                  const int4* __restrict__ node_meta, const float4* __restrict__ root,
                   const char* __restrict__ peer_pub, const int world, const int rank, const float theta2,
-                  uint32_t* __restrict__ visit, float4* __restrict__ let_out, int* __restrict__ let_cnt, const int cap_let) {
+                  uint32_t* __restrict__ frontier, const int cap, int* __restrict__ fr_count, float4* __restrict__ let_out,
+                  int* __restrict__ let_cnt, const int cap_let) {
   cg::grid_group grid = cg::this_grid();
   const float root_half = root[0].w;
-  for (int gen = 0; gen <= kMaxLevel; gen++) {
-  const int gb = c->gen_off[gen], ge = c->gen_off[gen + 1];
-  if (gb >= ge) break;
-  for (int node = gb + blockIdx.x * blockDim.x + threadIdx.x; node < ge; node += gridDim.x * blockDim.x) {
-    const uint32_t mask = node == 0 ? (((1u << world) - 1u) & ~(1u << rank)) : visit[node];
-    const int4 m = node_meta[node];
-    const bool leaf = (m.z & kLeafFlag) != 0;
-    uint32_t down = 0;
-    if (mask) {
+  const uint32_t all_peers = ((1u << world) - 1u) & ~(1u << rank);
+  for (int gen = 0; gen <= kMaxLevel + 1; gen++) {
+    const int cur = gen & 1, nxt = cur ^ 1;
+    const uint32_t* fnode = frontier + (size_t)cur * 2 * cap;
+    const uint32_t* fmask = fnode + cap;
+    uint32_t* nnode = frontier + (size_t)nxt * 2 * cap;
+    uint32_t* nmask = nnode + cap;
+    const int count = *((volatile int*)&fr_count[cur]);
+    if (count <= 0) break;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+      const int node = (int)fnode[i];
+      const uint32_t mask = gen == 0 ? all_peers : fmask[i];
+      const int4 m = node_meta[node];
+      const bool leaf = (m.z & kLeafFlag) != 0;
       const float4 cm = node_com[node];
       const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);
       const float need = size * size / fmaxf(theta2, 1e-30f);      // accepted  <=>  distance^2 > need
       const bool single = leaf && m.y == 1;
+      uint32_t down = 0;
       for (int p = 0; p < world; p++) {
         if (!(mask >> p & 1u)) continue;
         const bool accept = single || (theta2 > 0.f && let_accept_for_peer(cm, need, peer_pub + (size_t)p * kPubBytes));
@@ -1249,10 +1258,14 @@ let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ no
           down |= 1u << p;
         }
       }
+      if (down) {
+        const int slot = atomicAdd(&fr_count[nxt], m.y);
+        for (int k = 0; k < m.y; k++) if (slot + k < cap) { nnode[slot + k] = (uint32_t)(m.x + k); nmask[slot + k] = down; }
+      }
     }
-    if (!leaf) for (int k = 0; k < m.y; k++) visit[m.x + k] = down;
-  }
-  grid.sync();
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) fr_count[cur] = 0;     // becomes the "next" counter of the generation after this one
+    grid.sync();
   }
 }
 
@@ -1377,15 +1390,13 @@ int bh_let_redistribute(BHState& st, Comm* comm, const BHParams& p, float4* posm
       return -5;
     }
   }
-  auto exchange = [&](const void* send, void* recv, size_t elem) -> int {
-    size_t a[kMaxWorld], b[kMaxWorld], c2[kMaxWorld], d[kMaxWorld];
-    for (int q = 0; q < world; q++) { a[q] = sb[q] * elem; b[q] = so[q] * elem; c2[q] = rb[q] * elem; d[q] = ro[q] * elem; }
-    return comm->all_to_all_v(send, a, b, recv, c2, d, s);
-  };
-  // destination-sorted bodies sit in *_b; every rank receives its new bodies into *_a
-  NB_TRY(exchange(posm_b, posm_a, 16));
-  NB_TRY(exchange(vel_b, vel_a, 16));
-  NB_TRY(exchange(ids_b, ids_a, 4));
+  // destination-sorted bodies sit in *_b; every rank receives its new bodies into *_a (one grouped exchange)
+  {
+    const void* sendv[3] = {posm_b, vel_b, ids_b};
+    void* recvv[3] = {posm_a, vel_a, ids_a};
+    const size_t elem[3] = {16, 16, 4};
+    NB_TRY(comm->all_to_all_v_multi(3, sendv, recvv, elem, sb, so, rb, ro, s));
+  }
   *n_local = (int)total;
   *n_stay = (int)rb[rank];
   NB_CUDA(cudaGetLastError());
@@ -1402,7 +1413,7 @@ int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* pos
   const int64_t need_nodes = std::max<int64_t>(m->cap_nodes, 16);
   if (need_nodes > m->cap_visit) {
     NB_CUDA(cudaStreamSynchronize(s));
-    NB_TRY(realloc_dev(&m->visit, (size_t)need_nodes));
+    NB_TRY(realloc_dev(&m->visit, (size_t)need_nodes * 4 + 4));
     m->cap_visit = need_nodes;
   }
   NB_CUDA(cudaMemsetAsync(m->send_off, 0, (size_t)(world + 1) * 4, s));
@@ -1414,11 +1425,17 @@ int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* pos
   NB_TRY(comm->all_gather_bytes(my_pub, m->peer_pub, kPubBytes, s));
   NB_CUDA(cudaMemsetAsync(m->let_cnt, 0, (size_t)world * 4, s));
   if (n > 0) {
-    int w = world, r = rank, cap_let = (int)m->cap_let;
+    int w = world, r = rank, cap_let = (int)m->cap_let, cap_fr = (int)m->cap_visit;
     float theta2 = p.theta * p.theta;
-    void* args[] = {(void*)&posm, &m->node_com, &m->node_meta, &m->counters, &m->root, &m->peer_pub, &w, &r, &theta2, &m->visit,
+    int* fr_count = reinterpret_cast<int*>(m->visit + (size_t)m->cap_visit * 4);
+    static const int init_count[2] = {1, 0};
+    NB_CUDA(cudaMemsetAsync(m->visit, 0, 4, s));                                    // frontier[0] = the root
+    NB_CUDA(cudaMemcpyAsync(fr_count, init_count, sizeof(init_count), cudaMemcpyHostToDevice, s));
+    void* args[] = {(void*)&posm, &m->node_com, &m->node_meta, &m->root, &m->peer_pub, &w, &r, &theta2, &m->visit, &cap_fr, &fr_count,
                     &m->let_out, &m->let_cnt, &cap_let};
-    NB_CUDA(cudaLaunchCooperativeKernel((void*)let_export_kernel, dim3(sm_count()), dim3(256), args, 0, s));
+    int per_sm = 1;
+    NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, let_export_kernel, 256, 0));
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)let_export_kernel, dim3(sm_count() * std::max(1, std::min(per_sm, 4))), dim3(256), args, 0, s));
     *launches += 1;
   }
   // one message per rank: [world + 1] migration offsets | [world] export counts; one all-gather, one host read

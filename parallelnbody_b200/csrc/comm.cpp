@@ -124,6 +124,22 @@ class NcclComm : public Comm {
     return 0;
   }
 
+  int all_to_all_v_multi(int nbuf, const void* const* send, void* const* recv, const size_t* elem, const size_t* send_cnt,
+                         const size_t* send_off, const size_t* recv_cnt, const size_t* recv_off, cudaStream_t s) override {
+    NB_NCCL(api()->GroupStart(), "ncclGroupStart");
+    ncclResult_t bad = ncclSuccess;
+    const char* where = "";
+    for (int k = 0; k < nbuf && bad == ncclSuccess; k++)
+      for (int p = 0; p < world_ && bad == ncclSuccess; p++) {
+        if (send_cnt[p]) { bad = api()->Send((const char*)send[k] + send_off[p] * elem[k], send_cnt[p] * elem[k], ncclInt8, p, comm_, s); where = "ncclSend"; }
+        if (bad == ncclSuccess && recv_cnt[p]) { bad = api()->Recv((char*)recv[k] + recv_off[p] * elem[k], recv_cnt[p] * elem[k], ncclInt8, p, comm_, s); where = "ncclRecv"; }
+      }
+    const ncclResult_t end = api()->GroupEnd();
+    if (bad != ncclSuccess) return fail(bad, where);
+    NB_NCCL(end, "ncclGroupEnd");
+    return 0;
+  }
+
  private:
   ncclComm_t comm_ = nullptr;
 };
@@ -282,6 +298,17 @@ class LoopComm : public Comm {
 };
 
 }  // namespace
+
+// Default: one exchange per buffer (the loop-back back end); NcclComm overrides it with a single group.
+int Comm::all_to_all_v_multi(int nbuf, const void* const* send, void* const* recv, const size_t* elem, const size_t* send_cnt,
+                             const size_t* send_off, const size_t* recv_cnt, const size_t* recv_off, cudaStream_t s) {
+  size_t a[64], b[64], c[64], d[64];
+  for (int k = 0; k < nbuf; k++) {
+    for (int p = 0; p < world_; p++) { a[p] = send_cnt[p] * elem[k]; b[p] = send_off[p] * elem[k]; c[p] = recv_cnt[p] * elem[k]; d[p] = recv_off[p] * elem[k]; }
+    NB_TRY(all_to_all_v(send[k], a, b, recv[k], c, d, s));
+  }
+  return 0;
+}
 
 int Comm::unique_id(uint8_t out128[128]) {
   NB_TRY(ready());

@@ -36,6 +36,10 @@ class Comm {
   // must not overlap.
   virtual int all_to_all_v(const void* send, const size_t* send_bytes, const size_t* send_off, void* recv,
                            const size_t* recv_bytes, const size_t* recv_off, cudaStream_t s) = 0;
+  // Several all_to_all_v with the same per-peer ELEMENT counts / offsets in one go (bodies travel as positions,
+  // velocities and ids): elem[k] bytes per element of buffer pair k. One NCCL group = one launch.
+  virtual int all_to_all_v_multi(int nbuf, const void* const* send, void* const* recv, const size_t* elem, const size_t* send_cnt,
+                                 const size_t* send_off, const size_t* recv_cnt, const size_t* recv_off, cudaStream_t s);
 
  protected:
   int rank_ = 0, world_ = 1;
