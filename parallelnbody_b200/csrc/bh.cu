@@ -1198,16 +1198,16 @@ __device__ __forceinline__ bool let_accept_for_peer(const float4 cm, const float
     const int b = stack[--sp];
     const int2 ch = child[b];
     if (ch.y == 0) return false;                    // too close to a cell the peer does not describe any finer
-    // children that are still too close, nearest last (= popped first)
-    float dk[8];
-    int nk = 0, idx[8];
+    // children that are still too close; the nearest one goes on top (popped first)
+    int nk = 0, idx[8], kmin = 0;
+    float dmin = 3.0e38f;
     for (int k = 0; k < ch.y; k++) {
       const float d = dist2(ch.x + k);
       if (d > need) continue;
-      int q = nk++;
-      while (q > 0 && dk[q - 1] < d) { dk[q] = dk[q - 1]; idx[q] = idx[q - 1]; q--; }
-      dk[q] = d; idx[q] = ch.x + k;
+      if (d < dmin) { dmin = d; kmin = nk; }
+      idx[nk++] = ch.x + k;
     }
+    if (nk > 0) { const int t = idx[kmin]; idx[kmin] = idx[nk - 1]; idx[nk - 1] = t; }
     if (sp + nk > 96) return false;                 // cannot happen for a 21-level tree; stay conservative
     for (int k = 0; k < nk; k++) stack[sp++] = idx[k];
   }
@@ -1227,6 +1227,8 @@ let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ no
   cg::grid_group grid = cg::this_grid();
   const float root_half = root[0].w;
   const uint32_t all_peers = ((1u << world) - 1u) & ~(1u << rank);
+  int wpad = 1;
+  while (wpad < world) wpad <<= 1;
   for (int gen = 0; gen <= kMaxLevel + 1; gen++) {
     const int cur = gen & 1, nxt = cur ^ 1;
     const uint32_t* fnode = frontier + (size_t)cur * 2 * cap;
@@ -1235,18 +1237,26 @@ let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ no
     uint32_t* nmask = nnode + cap;
     const int count = *((volatile int*)&fr_count[cur]);
     if (count <= 0) break;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-      const int node = (int)fnode[i];
-      const uint32_t mask = gen == 0 ? all_peers : fmask[i];
-      const int4 m = node_meta[node];
-      const bool leaf = (m.z & kLeafFlag) != 0;
-      const float4 cm = node_com[node];
-      const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);
-      const float need = size * size / fmaxf(theta2, 1e-30f);      // accepted  <=>  distance^2 > need
-      const bool single = leaf && m.y == 1;
+    // one thread per (frontier cell, peer): wpad = world rounded up to a power of two lanes share a cell, so the descents
+    // of one cell through its peers' boundary trees run side by side and are combined with shuffles
+    const long long total = (long long)count * wpad;
+    for (long long t0 = (long long)(blockIdx.x * blockDim.x + (threadIdx.x & ~31)); t0 < total; t0 += (long long)gridDim.x * blockDim.x) {
+      const long long t = t0 + (threadIdx.x & 31);
+      const int i = (int)(t / wpad), p = (int)(t % wpad);
+      const bool live = t < total;
+      int node = 0;
+      uint32_t mask = 0;
+      if (live) { node = (int)fnode[i]; mask = gen == 0 ? all_peers : fmask[i]; }
+      const bool mine = live && p < world && (mask >> p & 1u);
+      int4 m = make_int4(0, 0, 0, 0);
+      bool leaf = false;
       uint32_t down = 0;
-      for (int p = 0; p < world; p++) {
-        if (!(mask >> p & 1u)) continue;
+      if (live) { m = node_meta[node]; leaf = (m.z & kLeafFlag) != 0; }
+      if (mine) {
+        const float4 cm = node_com[node];
+        const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);
+        const float need = size * size / fmaxf(theta2, 1e-30f);      // accepted  <=>  distance^2 > need
+        const bool single = leaf && m.y == 1;
         const bool accept = single || (theta2 > 0.f && let_accept_for_peer(cm, need, peer_pub + (size_t)p * kPubBytes));
         if (accept) {
           const int slot = atomicAdd(let_cnt + p, 1);
@@ -1255,10 +1265,12 @@ let_export_kernel(const float4* __restrict__ posm, const float4* __restrict__ no
           const int slot = atomicAdd(let_cnt + p, m.y);
           for (int k = 0; k < m.y; k++) if (slot + k < cap_let) let_out[(size_t)p * cap_let + slot + k] = posm[m.x + k];
         } else {
-          down |= 1u << p;
+          down = 1u << p;
         }
       }
-      if (down) {
+      __syncwarp();
+      for (int o = 1; o < wpad; o <<= 1) down |= __shfl_xor_sync(0xffffffffu, down, o);
+      if (live && p == 0 && down) {
         const int slot = atomicAdd(&fr_count[nxt], m.y);
         for (int k = 0; k < m.y; k++) if (slot + k < cap) { nnode[slot + k] = (uint32_t)(m.x + k); nmask[slot + k] = down; }
       }
