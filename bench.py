@@ -280,7 +280,7 @@ def load_traffic(kernel: str, workload: str):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_baseline=False):
+def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_baseline=False, e2e=True):
     """One workload on the product path: device-resident timing, end-to-end timing, roofline. Returns the dict of results
     (rank 0) or None."""
     import torch
@@ -335,6 +335,16 @@ def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_basel
     let_phases_min = {k[7:]: -max_over_ranks(-let_ms[k] / steps) for k in LET_KEYS}
 
     # ---- end to end through the public API with HOST buffers (pinned FParticle arrays in, Tick, FParticle arrays out)
+    if not e2e:
+        stats = sim.Stats()
+        sim.close()
+        if rank != 0:
+            return None
+        return {"metric": "Barnes-Hut steps/s", "value": steps / (ms_total_max * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": steps,
+                "ms_per_step": ms_total_max / steps, "config": workload_config(args, wl, world, name),
+                "phases_ms_per_step": {k: ms[k] / steps for k in ("force", "build", "integrate", "comm")}, "clocks": clk,
+                "interactions_per_body": inter_all / steps / n, "sort_passes": stats["sort_passes"],
+                "tree": {"nodes": stats["tree_nodes"], "depth": stats["tree_depth"], "walk_groups": stats["walk_groups"]}}
     aos_in = torch.empty(n * 40, dtype=torch.uint8).pin_memory()
     aos_out = torch.empty(n * 40, dtype=torch.uint8).pin_memory()
     aos_in.numpy().view(P.PARTICLE_DTYPE)[:] = to_particles(posm, vel)
@@ -484,6 +494,12 @@ def run_ours(args):
                           with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         if rank == 0:
             line["bh"] = bh
+        if world == 1 and not args.no_bh_baseline:
+            # the multi-GPU Barnes-Hut workload (BASELINE configs[4]) on ONE GPU, device-resident: the denominator of its
+            # strong-scaling efficiency at N = 2 / 4 / 8
+            b16 = run_workload(args, "two_galaxies_16m_bh", ctx, 20, 3, min_seconds=1.0, with_cpu_baseline=False, e2e=False)
+            if rank == 0:
+                line["bh_multi_gpu_workload_on_1_gpu"] = b16
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -502,6 +518,7 @@ def main():
                     help="multi-GPU Barnes-Hut: 0 = Morton domain split + LET exchange, 1 = replicated tree")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bh", action="store_true", help="skip the Barnes-Hut object of the default run")
+    ap.add_argument("--no-bh-baseline", action="store_true", help="1 GPU: skip the 16M-body Barnes-Hut scaling baseline")
     ap.add_argument("--no-extras", action="store_true", help="reference arm: skip the full-Tick and Barnes-Hut figures")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
