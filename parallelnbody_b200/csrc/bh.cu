@@ -663,6 +663,292 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
   if (lane == 0 && inter) atomicAdd(&c->interactions, inter);
 }
 
+// ---- K8a': the same walk, warp-specialised ---------------------------------------------------------------------
+// The walk above alternates, inside every warp, a latency-bound traversal (dependent smem / L2 accesses, scans) with an
+// FMA-pipe-bound evaluation, so the FMA pipe idles whenever a scheduler's warps are traversing at the same time (ncu: 68 %
+// busy). Here the two halves run in different warps: warps 0..3 of a CTA TRAVERSE (one group each, exactly the rule and
+// order of the kernel above) and stream what they accept through a shared-memory ring of kWsChunks x 64 entries to
+// warps 4..7, which hold the groups' bodies in registers and only EVALUATE. Hand-off per 64-entry chunk through a pair
+// of mbarriers (full / empty, one elected lane arrives, every lane of the other warp waits); a chunk carries its group and
+// a LAST flag, so the evaluating warp writes the accelerations when the group ends. One producer feeds one consumer, chunks
+// are consumed in order: the summation order - hence the result - is that of the single-warp kernel, bit for bit.
+constexpr int kWsPairs = 4;
+constexpr int kWsThreads = 64 * kWsPairs;
+constexpr int kWsChunk = 64;
+constexpr int kWsChunks = 4;
+constexpr int kWsLast = 1 << 16;
+// register split between the two warpgroups of a CTA (launch: 64 per thread; setmaxnreg moves the budget to where the
+// instruction-level parallelism pays - the evaluation keeps eight interaction chains in flight per warp)
+template <int SPLIT> struct WsRegs { static constexpr int traverse = SPLIT == 1 ? 40 : 48, evaluate = SPLIT == 1 ? 88 : 80; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, const int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, const uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int B, bool EPS0>
+__device__ __forceinline__ void eval_chunk(const float* __restrict__ ch, const int count, const float2 (&nx)[B], const float2 (&ny)[B],
+                                           const float2 (&nz)[B], const float2 eps2, float2 (&ax)[B], float2 (&ay)[B], float2 (&az)[B]) {
+#pragma unroll 2
+  for (int j = 0; j < count; j += 4) {
+    const float4 X = *reinterpret_cast<const float4*>(ch + j);
+    const float4 Y = *reinterpret_cast<const float4*>(ch + kWsChunk + j);
+    const float4 Z = *reinterpret_cast<const float4*>(ch + 2 * kWsChunk + j);
+    const float4 M = *reinterpret_cast<const float4*>(ch + 3 * kWsChunk + j);
+#pragma unroll
+    for (int k = 0; k < B; k++) {
+      interact2<EPS0>(f2(X.x, X.y), f2(Y.x, Y.y), f2(Z.x, Z.y), f2(M.x, M.y), nx[k], ny[k], nz[k], eps2, ax[k], ay[k], az[k]);
+      interact2<EPS0>(f2(X.z, X.w), f2(Y.z, Y.w), f2(Z.z, Z.w), f2(M.z, M.w), nx[k], ny[k], nz[k], eps2, ax[k], ay[k], az[k]);
+    }
+  }
+}
+
+template <int B, bool EPS0, int SPLIT>
+__global__ void __launch_bounds__(kWsThreads, B <= 2 ? 4 : 2)
+bh_walk_ws_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com, const int4* __restrict__ node_meta,
+                  const float4* __restrict__ tgt, const int2* __restrict__ groups, Counters* __restrict__ c,
+                  const float4* __restrict__ root, const float theta2, const float eps2, const float G, const int t0,
+                  const int t1, const int accumulate, int* __restrict__ stacks, float4* __restrict__ acc,
+                  int* __restrict__ group_cost, uint32_t* __restrict__ bin_cost, const int n_targets) {
+  __shared__ __align__(16) float ring_all[kWsPairs][kWsChunks * 4 * kWsChunk];   // chunk-major: x[64] | y[64] | z[64] | m[64]
+  __shared__ int stk_all[kWsPairs][kStackSmem];
+  __shared__ int offs_all[kWsPairs][32];
+  __shared__ int2 info_all[kWsPairs][kWsChunks];               // (group, entries | LAST) of a chunk; group < 0 = no more work
+  __shared__ __align__(8) uint64_t full_all[kWsPairs][kWsChunks], empty_all[kWsPairs][kWsChunks];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, w = warp % kWsPairs;
+  if (threadIdx.x < kWsPairs * kWsChunks) {
+    mbar_init(&full_all[0][0] + threadIdx.x, 1);
+    mbar_init(&empty_all[0][0] + threadIdx.x, 1);
+  }
+  __syncthreads();
+  float* ring = ring_all[w];
+  int2* info = info_all[w];
+  uint64_t* full = full_all[w];
+  uint64_t* empty = empty_all[w];
+
+  if (warp >= kWsPairs) {
+    // ------------------------------------------------------------------ evaluating warp
+    if (SPLIT > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WsRegs<SPLIT>::evaluate));
+    const float2 eps2v = f2(eps2, eps2);
+    float2 nx[B], ny[B], nz[B], ax[B], ay[B], az[B];
+    int2 r = make_int2(0, 0);
+    int cur = -1;
+    for (unsigned q = 0;; q++) {
+      const int ch = q & (kWsChunks - 1);
+      mbar_wait(full + ch, (q / kWsChunks) & 1);
+      const int2 inf = info[ch];
+      if (inf.x < 0) break;
+      if (inf.x != cur) {
+        cur = inf.x;
+        r = groups[cur];
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+          ax[k] = f2(0.f, 0.f); ay[k] = f2(0.f, 0.f); az[k] = f2(0.f, 0.f);
+          const int i = r.x + lane + 32 * k;
+          const float4 p = tgt[i < r.y ? i : r.x];
+          nx[k] = f2(-p.x, -p.x); ny[k] = f2(-p.y, -p.y); nz[k] = f2(-p.z, -p.z);
+        }
+      }
+      eval_chunk<B, EPS0>(ring + ch * (4 * kWsChunk), inf.y & (kWsLast - 1), nx, ny, nz, eps2v, ax, ay, az);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + ch);
+      if (inf.y & kWsLast) {
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+          const int i = r.x + lane + 32 * k;
+          if (i < r.y && i >= t0 && i < t1) {
+            float4 a = make_float4(G * (ax[k].x + ax[k].y), G * (ay[k].x + ay[k].y), G * (az[k].x + az[k].y), 0.f);
+            if (accumulate) { const float4 o = acc[i]; a.x += o.x; a.y += o.y; a.z += o.z; }
+            acc[i] = a;
+          }
+        }
+        cur = -1;
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- traversing warp
+  if (SPLIT > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WsRegs<SPLIT>::traverse));
+  int* stk = stk_all[w];
+  int* offs = offs_all[w];
+  int* gstack = stacks + (size_t)(blockIdx.x * kWsPairs + w) * kStackCap;
+  const int ngroups = c->ngroups;
+  const float root_half = root[0].w;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned long long inter = 0;
+  unsigned wpos = 0;             // entries written so far (chunk = wpos / 64)
+  unsigned acq = 0, done = 0;    // chunks acquired for writing / handed over
+  int g = 0;
+  // every chunk up to the one holding entry `upto` must have been released by the evaluating warp
+  auto ensure = [&](const unsigned upto) {
+    const unsigned need = upto / kWsChunk + 1;
+    while (acq < need) { mbar_wait(empty + (acq & (kWsChunks - 1)), ((acq / kWsChunks) & 1) ^ 1); acq++; }
+  };
+  auto put = [&](const unsigned pos, const float4 v) {
+    float* d = ring + ((pos / kWsChunk) & (kWsChunks - 1)) * (4 * kWsChunk) + (pos & (kWsChunk - 1));
+    d[0] = v.x; d[kWsChunk] = v.y; d[2 * kWsChunk] = v.z; d[3 * kWsChunk] = v.w;
+  };
+  auto commit = [&]() {   // hand over the chunks that filled up
+    while (done < wpos / kWsChunk) {
+      __syncwarp();
+      if (lane == 0) { info[done & (kWsChunks - 1)] = make_int2(g, kWsChunk); mbar_arrive(full + (done & (kWsChunks - 1))); }
+      done++;
+    }
+  };
+  while (true) {
+    if (lane == 0) g = atomicAdd(&c->next_group, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= ngroups) break;
+    const int2 r = groups[g];
+    const int ntarget = min(r.y, t1) - max(r.x, t0);
+    if (ntarget <= 0) continue;
+    float lox = 3.4e38f, loy = 3.4e38f, loz = 3.4e38f, hix = -3.4e38f, hiy = -3.4e38f, hiz = -3.4e38f;
+#pragma unroll
+    for (int k = 0; k < B; k++) {
+      const int i = r.x + lane + 32 * k;
+      const float4 p = tgt[i < r.y ? i : r.x];
+      lox = fminf(lox, p.x); loy = fminf(loy, p.y); loz = fminf(loz, p.z);
+      hix = fmaxf(hix, p.x); hiy = fmaxf(hiy, p.y); hiz = fmaxf(hiz, p.z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+      loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+      loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+    }
+    const float gcx = 0.5f * (lox + hix), gcy = 0.5f * (loy + hiy), gcz = 0.5f * (loz + hiz);
+    const float ghx = 0.5f * (hix - lox), ghy = 0.5f * (hiy - loy), ghz = 0.5f * (hiz - loz);
+
+    int top = 1, base = 0;
+    int leaf_first = 0, leaf_excl = 0, ltotal = 0, lpos = 0;
+    if (lane == 0) stk[0] = 0;
+    __syncwarp();
+    const unsigned wstart = wpos;
+    bool overflow = false;
+    while (true) {
+      if (lpos < ltotal) {   // stream the next 32 bodies of the leaves opened by the last round
+        const int j = lpos + lane;
+        int L = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) if (offs[L + step] <= j) L += step;
+        const int first = __shfl_sync(0xffffffffu, leaf_first, L), off = __shfl_sync(0xffffffffu, leaf_excl, L);
+        const int cnt = min(32, ltotal - lpos);
+        float4 bd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < cnt) bd = posm[first + (j - off)];
+        ensure(wpos + cnt - 1);
+        if (lane < cnt) put(wpos + lane, bd);
+        wpos += cnt;
+        lpos += 32;
+      } else if (top > 0) {
+        if (top == base) {   // window empty: bring the youngest spilled entries back
+          const int cnt = min(base, kStackSmem / 2);
+          for (int k = lane; k < cnt; k += 32) stk[(base - cnt + k) & kStackMask] = gstack[base - cnt + k];
+          base -= cnt;
+          __syncwarp();
+        }
+        const int nb = min(32, top - base);
+        top -= nb;
+        const int e = lane < nb ? stk[(top + lane) & kStackMask] : -1;
+        float4 item = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool has_item = false;
+        int push_first = 0, push_n = 0, leaf_n = 0;
+        leaf_first = 0;
+        if (e >= 0) {
+          const float4 cm = node_com[e];
+          const int4 m = node_meta[e];
+          const bool leaf = (m.z & kLeafFlag) != 0;
+          const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);
+          const float dx = fmaxf(fabsf(cm.x - gcx) - ghx, 0.f), dy = fmaxf(fabsf(cm.y - gcy) - ghy, 0.f),
+                      dz = fmaxf(fabsf(cm.z - gcz) - ghz, 0.f);
+          const float dmin2 = dx * dx + dy * dy + dz * dz;
+          if (size * size < theta2 * dmin2 || (leaf && m.y == 1)) { item = cm; has_item = true; }
+          else if (leaf) { leaf_first = m.x; leaf_n = m.y; }
+          else { push_first = m.x; push_n = m.y; }
+        }
+        // a leaf too large for the packed scan below (a deepest-level cell full of coincident bodies): stream it on its own
+        unsigned big = __ballot_sync(0xffffffffu, leaf_n >= kLeafChunk);
+        while (big) {
+          const int src = __ffs(big) - 1;
+          big &= big - 1;
+          const int f = __shfl_sync(0xffffffffu, leaf_first, src), n = __shfl_sync(0xffffffffu, leaf_n, src);
+          for (int b0 = 0; b0 < n; b0 += 32) {
+            const int cnt = min(32, n - b0);
+            ensure(wpos + cnt - 1);
+            if (lane < cnt) put(wpos + lane, posm[f + b0 + lane]);
+            wpos += cnt;
+            commit();
+          }
+          if (lane == src) leaf_n = 0;
+        }
+        int incl = push_n | (leaf_n << 10);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int both = __shfl_sync(0xffffffffu, incl, 31);
+        const int total = both & 1023;
+        ltotal = both >> 10;
+        lpos = 0;
+        leaf_excl = (incl >> 10) - leaf_n;
+        if (ltotal) offs[lane] = leaf_excl;
+        if (total) {
+          const int need = (top - base) + total - kStackSmem;
+          if (need > 0) {
+            const int sp = min((need + 31) & ~31, top - base);
+            if (base + sp > kStackCap) { overflow = true; break; }
+            for (int k = lane; k < sp; k += 32) gstack[base + k] = stk[(base + k) & kStackMask];
+            base += sp;
+            __syncwarp();
+          }
+          const int dst = top + (incl & 1023) - push_n;
+#pragma unroll
+          for (int k = 0; k < 8; k++) if (k < push_n) stk[(dst + k) & kStackMask] = push_first + k;
+          top += total;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, has_item);
+        if (mask) {
+          const int na = __popc(mask);
+          ensure(wpos + na - 1);
+          if (has_item) put(wpos + __popc(mask & lt), item);
+          wpos += na;
+        }
+      } else {
+        break;
+      }
+      __syncwarp();
+      commit();
+    }
+    if (overflow && lane == 0) atomicExch(&c->overflow, 1);
+    // end of the group: pad the open chunk with massless entries up to a multiple of 4 and hand it over with the LAST flag
+    const unsigned long long entries = wpos - wstart;
+    {
+      const unsigned rem = wpos & (kWsChunk - 1), padded = (rem + 3) & ~3u;
+      ensure(wpos);
+      if (lane < padded - rem) put(wpos + lane, make_float4(0.f, 0.f, 0.f, 0.f));
+      __syncwarp();
+      if (lane == 0) { info[done & (kWsChunks - 1)] = make_int2(g, (int)padded | kWsLast); mbar_arrive(full + (done & (kWsChunks - 1))); }
+      done++;
+      wpos = done * kWsChunk;
+    }
+    inter += entries * (unsigned long long)ntarget;
+    if (group_cost && lane == 0) group_cost[g] = (accumulate ? group_cost[g] : 0) + (int)min(entries, 0x3fffffffull);
+    if (bin_cost && lane == 0)
+      atomicAdd(bin_cost + min((int)((long long)r.x * kCostBins / max(n_targets, 1)), kCostBins - 1), (uint32_t)min(entries * (unsigned long long)ntarget, 0xffffffffull));
+  }
+  ensure(wpos);
+  __syncwarp();
+  if (lane == 0) { info[done & (kWsChunks - 1)] = make_int2(-1, 0); mbar_arrive(full + (done & (kWsChunks - 1))); }
+  if (lane == 0 && inter) atomicAdd(&c->interactions, inter);
+}
+
 // ---- K8b: per-body walk with the reference's exact rule and order (parity mode) ---------------------------------
 // Octree::ComputeForces (OctreeSearch.h:99-108): d = |COM - x| (fp32 sqrtf); d == 0 -> skip; accept when Size / d < Theta or
 // one-body leaf: a += (float)(G * M / d^3) * (COM - x), scalar in double; else the children in octant order.
@@ -756,19 +1042,28 @@ __global__ void iota_kernel(int32_t* ids, int n, int first) {
 template <int B, bool EPS0>
 int launch_walk(Impl* m, Impl* g, const BHParams& p, const float4* posm, const float4* tgt, float4* acc, int t0, int t1,
                 bool accumulate, cudaStream_t s) {
+  // 0 = one warp traverses and evaluates (default: the faster one on B200, profiles/r2_walk_warp_specialised.md), 1 = warp-specialised
+  static const int mode = getenv("NBODY_WALK") ? atoi(getenv("NBODY_WALK")) : 0;
+  static const int split = getenv("NBODY_WS_SPLIT") ? atoi(getenv("NBODY_WS_SPLIT")) : 2;   // register split: 0 = 64/64, 1 = 40/88, 2 = 48/80
+  auto ws = split == 1 ? bh_walk_ws_kernel<B, EPS0, (B <= 2 ? 1 : 0)> : split == 2 ? bh_walk_ws_kernel<B, EPS0, (B <= 2 ? 2 : 0)> : bh_walk_ws_kernel<B, EPS0, 0>;
   int per_sm = 0;
-  NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<B, EPS0>, kWalkThreads, 0));
+  if (mode == 1) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ws, kWsThreads, 0));
+  else NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<B, EPS0>, kWalkThreads, 0));
   const int grid = sm_count() * std::max(1, std::min(per_sm, 8));
-  const int64_t need = (int64_t)grid * kWalkWarps * kStackCap;
+  const int64_t need = (int64_t)grid * (mode == 1 ? kWsPairs : kWalkWarps) * kStackCap;
   if (need > m->cap_stacks) {
     NB_CUDA(cudaStreamSynchronize(s));
     NB_TRY(realloc_dev(&m->stacks, (size_t)need));
     m->cap_stacks = need;
   }
   NB_CUDA(cudaMemsetAsync(&g->counters->next_group, 0, sizeof(int), s));
-  bh_walk_group_kernel<B, EPS0><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, tgt, g->groups, g->counters, m->root,
-                                                              p.theta * p.theta, p.eps2, p.G, t0, t1, accumulate ? 1 : 0,
-                                                              m->stacks, acc, g->group_cost, g->bin_cost, g->n);
+  if (mode == 1)
+    ws<<<grid, kWsThreads, 0, s>>>(posm, m->node_com, m->node_meta, tgt, g->groups, g->counters, m->root, p.theta * p.theta, p.eps2, p.G, t0, t1,
+                                   accumulate ? 1 : 0, m->stacks, acc, g->group_cost, g->bin_cost, g->n);
+  else
+    bh_walk_group_kernel<B, EPS0><<<grid, kWalkThreads, 0, s>>>(posm, m->node_com, m->node_meta, tgt, g->groups, g->counters, m->root,
+                                                                p.theta * p.theta, p.eps2, p.G, t0, t1, accumulate ? 1 : 0,
+                                                                m->stacks, acc, g->group_cost, g->bin_cost, g->n);
   return 0;
 }
 
