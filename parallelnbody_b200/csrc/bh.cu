@@ -48,7 +48,7 @@ constexpr int kMaxWorld = 16;
 constexpr int kCostBins = 1024;          // equal-count bins along the sorted bodies in which the walks record their work
 
 struct Counters {
-  int nnodes, ngroups, ticket, depth, next_group, overflow, pad0, pad1;
+  int nnodes, ngroups, ticket, depth, next_group, overflow, bar_count, bar_gen;   // bar_*: the split's own grid barrier
   int gen_off[kMaxLevel + 4];
   unsigned long long interactions;
 };
@@ -256,7 +256,7 @@ __global__ void tree_init_kernel(const uint64_t* __restrict__ keys, const int n,
   range[0] = make_int2(0, n);
   meta[0] = make_int4(0, 0, lvl, -1);
   ready[0] = 0;
-  c->nnodes = 1; c->ngroups = 0; c->ticket = 0; c->depth = 0; c->next_group = 0; c->overflow = 0;
+  c->nnodes = 1; c->ngroups = 0; c->ticket = 0; c->depth = 0; c->next_group = 0; c->overflow = 0; c->bar_count = 0; c->bar_gen = 0;
   for (int k = 0; k < kMaxLevel + 4; k++) c->gen_off[k] = 1;
   c->gen_off[0] = 0;
   c->interactions = 0;
@@ -364,14 +364,28 @@ __global__ void __launch_bounds__(256)
 tree_split_kernel(const uint64_t* __restrict__ keys, const int leaf_size, const int group_size, const int super, const int levels,
                   int2* __restrict__ range, int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
                   Counters* __restrict__ c) {
-  cg::grid_group grid = cg::this_grid();
+  // One grid-wide barrier per generation, written out here instead of cg::grid::sync() (which would need a second one
+  // so that nobody allocates nodes again before everyone has read the count): the LAST block to arrive records how many
+  // nodes exist - everything the generation created - in gen_off and only then releases the others, who read it there.
+  // The launch is cooperative, so all blocks are co-resident and the spin cannot starve anyone.
   int gb = 0, ge = 1, maxlvl = 0, gen = 0;
   for (; gen <= kMaxLevel; gen++) {
     maxlvl = max(maxlvl, split_generation(gb, ge, keys, leaf_size, group_size, super, levels, range, meta, ready, groups, c));
-    grid.sync();
-    const int next = *((volatile int*)&c->nnodes);   // everything this generation created
-    grid.sync();                                     // nobody allocates again before everyone has read it
-    if (blockIdx.x == 0 && threadIdx.x == 0) c->gen_off[gen + 2] = next;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const int arrived = atomicAdd(&c->bar_count, 1) + 1;
+      if (arrived == (int)gridDim.x * (gen + 1)) {
+        c->gen_off[gen + 2] = atomicAdd(&c->nnodes, 0);
+        __threadfence();
+        atomicExch(&c->bar_gen, gen + 1);
+      } else {
+        while (*((volatile int*)&c->bar_gen) < gen + 1) __nanosleep(20);
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    const int next = *((volatile int*)&c->gen_off[gen + 2]);
     gb = ge; ge = next;
     if (gb == ge) break;
   }
