@@ -392,10 +392,21 @@ def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_basel
                 "kernel": "bh_walk_group_kernel", "interactions_per_step": inter_all / steps,
                 "interactions_per_body": inter_all / steps / n, "flops_per_interaction": FLOPS_PER_INTERACTION,
                 "ms_per_launch": ms["force"] / steps,
+                "what": "raw: every (accepted cell or opened-leaf body) x group member the walk evaluates, 20 flop each; the "
+                        "group criterion opens more cells than the reference's per-body rule needs (reference_rule below)",
                 "build": {"bound": "hbm", "achieved": build_gbs, "peak": hbm, "unit": "GB/s", "frac": build_gbs / hbm,
                           "algorithmic_bytes": build_bytes, "ms": ms["build"] / steps,
                           "peak_kind": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback 6550.7 GB/s (B200_PROFILING.md)",
                           "what": "cube size + Morton keys + radix sort passes + body gather + tree split + monopoles, algorithmic bytes (DESIGN.md section 4)"}}
+    if method == "bh" and world == 1 and n <= (1 << 21):
+        # the same system walked per body with the reference's own rule (OctreeSearch.h:103, mac = 1, outside any timed region):
+        # how many interactions the reference would evaluate, hence the walk's rate in reference-rule-equivalent interactions
+        with P.OctreeSearch(method=meth, G=1e4, eps=eps, theta=theta, PhDeltaTime=dt, device=local_rank, mac=1, leaf_size=1) as ref_rule:
+            ref_rule.SetBodies(posm, vel)
+            ref_rule.CreateOctree()
+            per_body = ref_rule.Stats()["interactions"] / n
+        roof["reference_rule"] = {"interactions_per_body": per_body, "useful_fraction": per_body / (inter_all / steps / n),
+                                  "equivalent_interactions_per_s": per_body * n / (ms["force"] / steps * 1e-3)}
     if rank != 0:
         return None
     res = {

@@ -122,8 +122,11 @@ typedef struct nbody_sim nbody_sim; /* opaque handle: owns device buffers, strea
 /* ---- lifecycle ------------------------------------------------------------------------------------ */
 int nbody_abi_version(void);
 const char* nbody_last_error(void);
-/* Fill cfg with the reference's shipped values: method = BARNES_HUT, G = 1e4, eps = 0, theta = 1.0, dt = 0.01,
- * device 0, world 1, leaf_size 16, reference_root 0 (OctreeSearch.cpp:8,85; OctreeSearch.h:104). */
+/* Fill cfg with the reference's shipped PHYSICS: method = BARNES_HUT, G = 1e4, eps = 0, theta = 1.0, dt = 0.01
+ * (OctreeSearch.cpp:8,85; OctreeSearch.h:104), device 0, world 1 - and this library's production TREE SHAPE: leaf_size 16,
+ * group walk (mac 0), tight root cube (reference_root 0). That walk never accepts a cell the reference would open, so its
+ * forces are at least as accurate as the reference's at the same theta, but they are not bit-for-bit the reference's:
+ * the reference's own tree and visiting order are leaf_size 1, mac 1, reference_root 1 (the parity configuration). */
 int nbody_config_default(nbody_config* cfg);
 /* Replaces the actor's construction, AOctreeSearch::AOctreeSearch (OctreeSearch.cpp:8-12). */
 int nbody_create(nbody_sim** out, const nbody_config* cfg);
