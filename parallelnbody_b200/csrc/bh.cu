@@ -40,6 +40,7 @@ constexpr int kWalkMinCtas = 3;          // register budget: 80 per thread -> 24
 constexpr int kStackCap = 8192;          // per-warp spill slab of the walk stack (HBM/L2 resident; cells only, rarely touched)
 constexpr int kStackSmem = 512;          // per-warp stack window in shared memory
 constexpr int kStackMask = kStackSmem - 1;
+constexpr int kStackWin = 768;           // the single-warp walk's linear stack window (entries); a round pushes at most 256
 constexpr int kListCap = 128;            // per-warp interaction ring in shared memory
 constexpr int kFlush = 64;               // pending entries evaluated per flush (the ring also holds up to 32 more + 31 left over)
 constexpr int kLeafChunk = 1 << 16;      // leaves at least this large are streamed on their own (bounds the packed scan of the walk)
@@ -488,7 +489,7 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
   // posm / node_* = the SOURCE tree; tgt / groups / c = the targets and their walk groups (the same tree, or - for
   // the locally-essential points received from other ranks - the local tree whose bodies are being accelerated)
   __shared__ __align__(16) float ring_all[kWalkWarps][4 * kListCap];
-  __shared__ int stk_all[kWalkWarps][kStackSmem];   // top of the warp's cell stack; older entries spill to the global slab
+  __shared__ int stk_all[kWalkWarps][kStackWin];    // top of the warp's cell stack (a LINEAR window: entry i of the window at stk[i]); older entries spill to the global slab
   __shared__ int offs_all[kWalkWarps][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* ring = ring_all[w];
@@ -528,7 +529,8 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
     const float gcx = 0.5f * (lox + hix), gcy = 0.5f * (loy + hiy), gcz = 0.5f * (loz + hiz);
     const float ghx = 0.5f * (hix - lox), ghy = 0.5f * (hiy - loy), ghz = 0.5f * (hiz - loz);
 
-    // logical stack [0, top): entries [base, top) live in the shared-memory window (index & kStackMask), [0, base) in the slab
+    // logical stack = `base` spilled entries in the slab + the window stk[0 .. top); pushes are plain stores at stk[top + k]
+    // (no wrap-around arithmetic on the hot path; when the window fills up its oldest part moves to the slab and the rest slides down)
     int top = 1, base = 0, head = 0, pending = 0;
     int leaf_first = 0, leaf_excl = 0, ltotal = 0, lpos = 0;   // bodies of the leaves opened by the last round, being streamed
     if (lane == 0) stk[0] = 0;
@@ -553,16 +555,17 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
         }
         pending += cnt;
         lpos += 32;
-      } else if (top > 0) {
-        if (top == base) {   // window empty: bring the youngest spilled entries back
-          const int cnt = min(base, kStackSmem / 2);
-          for (int k = lane; k < cnt; k += 32) stk[(base - cnt + k) & kStackMask] = gstack[base - cnt + k];
+      } else if (top + base > 0) {
+        if (top == 0) {   // window empty: bring the youngest spilled entries back
+          const int cnt = min(base, kStackWin / 2);
+          for (int k = lane; k < cnt; k += 32) stk[k] = gstack[base - cnt + k];
           base -= cnt;
+          top = cnt;
           __syncwarp();
         }
-        const int nb = min(32, top - base);
+        const int nb = min(32, top);
         top -= nb;
-        const int e = lane < nb ? stk[(top + lane) & kStackMask] : -1;
+        const int e = lane < nb ? stk[top + lane] : -1;
         float4 item = make_float4(0.f, 0.f, 0.f, 0.f);
         bool has_item = false;
         int push_first = 0, push_n = 0, leaf_n = 0;
@@ -615,17 +618,23 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
         leaf_excl = (incl >> 10) - leaf_n;
         if (ltotal) offs[lane] = leaf_excl;
         if (total) {   // children of the opened cells go on the stack
-          const int need = (top - base) + total - kStackSmem;
-          if (need > 0) {   // make room: the oldest entries of the window move to the slab
-            const int sp = min((need + 31) & ~31, top - base);
+          if (top + total > kStackWin) {   // make room (rare): the oldest entries of the window move to the slab, the rest slides down
+            const int sp = min(top, max(kStackWin / 2, top + total - kStackWin));
             if (base + sp > kStackCap) { overflow = true; break; }
-            for (int k = lane; k < sp; k += 32) gstack[base + k] = stk[(base + k) & kStackMask];
+            for (int k = lane; k < sp; k += 32) gstack[base + k] = stk[k];
             base += sp;
             __syncwarp();
+            for (int k0 = 0; k0 < top - sp; k0 += 32) {
+              const int v = k0 + lane < top - sp ? stk[sp + k0 + lane] : 0;
+              __syncwarp();
+              if (k0 + lane < top - sp) stk[k0 + lane] = v;
+            }
+            top -= sp;
+            __syncwarp();
           }
-          const int dst = top + (incl & 1023) - push_n;
+          int* dst = stk + top + (incl & 1023) - push_n;
 #pragma unroll
-          for (int k = 0; k < 8; k++) if (k < push_n) stk[(dst + k) & kStackMask] = push_first + k;
+          for (int k = 0; k < 8; k++) if (k < push_n) dst[k] = push_first + k;
           top += total;
         }
         // accepted cells join the pending interaction ring
