@@ -305,7 +305,7 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
     // first body whose digit at this level is >= sub: 8-ary search (7 independent probes per round, so the chain of
     // dependent L2 round trips is log8 of the range), then a binary search on the last few bodies
     int lo = r.x, hi = split ? r.y : r.x;
-    while (hi - lo > 16) {
+    while (hi - lo > 7) {
       const int w = (hi - lo) >> 3;
       int d[7];
 #pragma unroll
@@ -321,9 +321,15 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
       }
       lo = nlo; hi = nhi;
     }
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((int)((keys[mid] >> shift) & 7ull) < sub) lo = mid + 1; else hi = mid;
+    if (lo < hi) {   // <= 7 candidates left: probe them all at once (independent loads) instead of a dependent binary search
+      const int len = hi - lo;
+      int d[7];
+#pragma unroll
+      for (int k = 0; k < 7; k++) d[k] = k < len ? (int)((keys[lo + k] >> shift) & 7ull) : 8;
+      int first = len;
+#pragma unroll
+      for (int k = 6; k >= 0; k--) if (d[k] >= sub) first = k;
+      lo += min(first, len);
     }
     __syncwarp();
     const int start = lo;
@@ -366,7 +372,7 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
   return maxlvl;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 tree_split_kernel(const uint64_t* __restrict__ keys, const int leaf_size, const int group_size, const int super, const int levels,
                   int2* __restrict__ range, int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
                   Counters* __restrict__ c) {
