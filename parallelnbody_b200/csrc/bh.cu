@@ -71,10 +71,7 @@ struct Impl {
   float4* node_bmin = nullptr;       // bounding box of every node's bodies (domain-split mode only)
   float4* node_bmax = nullptr;
   int64_t cap_boxes_nodes = 0;
-  int2* groups = nullptr;            // walk groups: body ranges of <= group_size neighbours, in the order the split emitted them
-  int2* groups_sorted = nullptr;     // the same in Morton order (they tile [0, n)): consecutive entries are spatial neighbours
-  uint32_t* group_bits = nullptr;    // one bit per body: set where a walk group starts | [cap / 1024 + 1] partial counts
-  int64_t cap_group_bits = 0;        // words of the bit map
+  int2* groups = nullptr;            // walk groups: body ranges of <= group_size neighbours
   int* group_cost = nullptr;         // interaction-list length of each group in the last walk (work measure for the domain split)
   Counters* counters = nullptr;
   float4* root = nullptr;          // [0] = cube (centre, half-width); [1] = previous root COM (xyz) + valid flag (w)
@@ -140,9 +137,6 @@ int ensure(Impl* m, int n, cudaStream_t s) {
   NB_TRY(realloc_dev(&m->node_range, nodes));
   NB_TRY(realloc_dev(&m->node_ready, nodes));
   NB_TRY(realloc_dev(&m->groups, c));
-  NB_TRY(realloc_dev(&m->groups_sorted, c));
-  m->cap_group_bits = (int64_t)(c / 32 + 2);
-  NB_TRY(realloc_dev(&m->group_bits, (size_t)m->cap_group_bits + (size_t)m->cap_group_bits / 1024 + 2));
   NB_TRY(realloc_dev(&m->group_cost, c));
   m->cap_nodes = (int64_t)nodes;
   m->cap_n = (int64_t)c;
@@ -252,21 +246,18 @@ __device__ __forceinline__ int common_levels(uint64_t a, uint64_t b) {
 
 // Cuts the body range [b, e) into ceil(len / group_size) near-equal walk groups.
 __device__ __forceinline__ void emit_groups(const int b, const int e, const int group_size, int2* __restrict__ groups,
-                                            uint32_t* __restrict__ gbits, Counters* __restrict__ c) {
+                                            Counters* __restrict__ c) {
   const int len = e - b;
   if (len <= 0) return;
   const int chunks = (len + group_size - 1) / group_size;
   const int g0 = atomicAdd(&c->ngroups, chunks);
-  for (int k = 0; k < chunks; k++) {
-    const int gb = b + (int)((long long)len * k / chunks);
-    groups[g0 + k] = make_int2(gb, b + (int)((long long)len * (k + 1) / chunks));
-    atomicOr(gbits + (gb >> 5), 1u << (gb & 31));   // the groups tile [0, n): their starts, as a bit map, give them in Morton order
-  }
+  for (int k = 0; k < chunks; k++)
+    groups[g0 + k] = make_int2(b + (int)((long long)len * k / chunks), b + (int)((long long)len * (k + 1) / chunks));
 }
 
 __global__ void tree_init_kernel(const uint64_t* __restrict__ keys, const int n, const int group_size, const int super, int2* __restrict__ range,
                                  int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
-                                 uint32_t* __restrict__ gbits, Counters* __restrict__ c) {
+                                 Counters* __restrict__ c) {
   const int lvl = n > 1 ? common_levels(keys[0], keys[n - 1]) : kMaxLevel;
   range[0] = make_int2(0, n);
   meta[0] = make_int4(0, 0, lvl, -1);
@@ -275,7 +266,7 @@ __global__ void tree_init_kernel(const uint64_t* __restrict__ keys, const int n,
   for (int k = 0; k < kMaxLevel + 4; k++) c->gen_off[k] = 1;
   c->gen_off[0] = 0;
   c->interactions = 0;
-  if (n <= super) emit_groups(0, n, group_size, groups, gbits, c);
+  if (n <= super) emit_groups(0, n, group_size, groups, c);
 }
 
 // The top-down split, all generations in ONE cooperative launch (grid-wide barrier between generations): every node
@@ -286,7 +277,7 @@ __global__ void tree_init_kernel(const uint64_t* __restrict__ keys, const int n,
 __device__ __forceinline__ int split_generation(const int gb, const int ge, const uint64_t* __restrict__ keys, const int leaf_size,
                                                 const int group_size, const int super, const int levels, int2* __restrict__ range,
                                                 int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
-                                                uint32_t* __restrict__ gbits, Counters* __restrict__ c) {
+                                                Counters* __restrict__ c) {
   const int lane = threadIdx.x & 31, sub = lane & 7, gshift = lane & ~7;
   const unsigned gmask = 0xffu << gshift;
   const int stride = gridDim.x * blockDim.x / 8;
@@ -304,7 +295,7 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
       if (sub == 0) {
         meta[node] = make_int4(r.x, cnt, level | kLeafFlag, m.w);
         // > super bodies in one deepest-level cell (coincident to the key resolution): walk them in chunks
-        if (cnt > super) emit_groups(r.x, r.y, group_size, groups, gbits, c);
+        if (cnt > super) emit_groups(r.x, r.y, group_size, groups, c);
       }
       int d = m.w >= 0 ? (meta[m.w].z & 255) + 1 : 0;   // depth of the leaf's cell in the reference's tree
       if (cnt > leaf_size && level < kMaxLevel) d = levels + 1;   // the sort was too shallow for this cell: ask for more next time
@@ -371,9 +362,9 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
         const int ck = __shfl_sync(0xffffffffu, cc, gshift + k), sk = __shfl_sync(0xffffffffu, start, gshift + k);
         if (!grouping || sub != 0 || ck == 0) continue;
         if (ck <= super) { if (run_end == run_begin) run_begin = sk; run_end = sk + ck; }
-        else { emit_groups(run_begin, run_end, group_size, groups, gbits, c); run_begin = run_end = 0; }
+        else { emit_groups(run_begin, run_end, group_size, groups, c); run_begin = run_end = 0; }
       }
-      if (grouping && sub == 0) emit_groups(run_begin, run_end, group_size, groups, gbits, c);
+      if (grouping && sub == 0) emit_groups(run_begin, run_end, group_size, groups, c);
     }
     if (split && sub == 0) meta[node] = make_int4(base, nchild, level, m.w);
   }
@@ -384,14 +375,14 @@ __device__ __forceinline__ int split_generation(const int gb, const int ge, cons
 __global__ void __launch_bounds__(256, 6)
 tree_split_kernel(const uint64_t* __restrict__ keys, const int leaf_size, const int group_size, const int super, const int levels,
                   int2* __restrict__ range, int4* __restrict__ meta, uint32_t* __restrict__ ready, int2* __restrict__ groups,
-                  uint32_t* __restrict__ gbits, Counters* __restrict__ c) {
+                  Counters* __restrict__ c) {
   // One grid-wide barrier per generation, written out here instead of cg::grid::sync() (which would need a second one
   // so that nobody allocates nodes again before everyone has read the count): the LAST block to arrive records how many
   // nodes exist - everything the generation created - in gen_off and only then releases the others, who read it there.
   // The launch is cooperative, so all blocks are co-resident and the spin cannot starve anyone.
   int gb = 0, ge = 1, maxlvl = 0, gen = 0;
   for (; gen <= kMaxLevel; gen++) {
-    maxlvl = max(maxlvl, split_generation(gb, ge, keys, leaf_size, group_size, super, levels, range, meta, ready, groups, gbits, c));
+    maxlvl = max(maxlvl, split_generation(gb, ge, keys, leaf_size, group_size, super, levels, range, meta, ready, groups, c));
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -412,59 +403,6 @@ tree_split_kernel(const uint64_t* __restrict__ keys, const int leaf_size, const 
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) for (int g = gen + 3; g < kMaxLevel + 4; g++) c->gen_off[g] = ge;
   if (maxlvl) atomicMax(&c->depth, maxlvl);
-}
-
-// ---- walk groups in Morton order --------------------------------------------------------------------------------
-// The split emits the walk groups in whatever order its warps get to them. They tile [0, n), so the bit map of their
-// first bodies (set by emit_groups) orders them: rank of a set bit = index of the group, next set bit = its end.
-constexpr int kBitsPerBlock = 1024;   // words of the bit map per CTA (256 threads x 4)
-__global__ void __launch_bounds__(256)
-group_bits_count_kernel(const uint32_t* __restrict__ bits, const int nwords, uint32_t* __restrict__ block_sums) {
-  __shared__ uint32_t wsum[8];
-  const int w0 = blockIdx.x * kBitsPerBlock + threadIdx.x * 4;
-  uint32_t cnt = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) if (w0 + k < nwords) cnt += __popc(bits[w0 + k]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += wsum[k]; block_sums[blockIdx.x] = t; }
-}
-
-__global__ void __launch_bounds__(256)
-group_sort_kernel(const uint32_t* __restrict__ bits, const int nwords, const uint32_t* __restrict__ block_sums, const int n,
-                  int* __restrict__ sorted /* int2 array seen as ints */) {
-  __shared__ uint32_t red[8];
-  __shared__ uint32_t s_base;
-  // groups in the blocks before this one
-  uint32_t before = 0;
-  for (int b = threadIdx.x; b < (int)blockIdx.x; b += 256) before += block_sums[b];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = before;
-  __syncthreads();
-  if (threadIdx.x == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += red[k]; s_base = t; }
-  __syncthreads();
-  const int w0 = blockIdx.x * kBitsPerBlock + threadIdx.x * 4;
-  uint32_t word[4], cnt = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) { word[k] = w0 + k < nwords ? bits[w0 + k] : 0u; cnt += __popc(word[k]); }
-  uint32_t total;
-  uint32_t rank = s_base + block_excl_scan(cnt, &total);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    uint32_t wd = word[k];
-    while (wd) {
-      const int pos = (w0 + k) * 32 + __ffs(wd) - 1;
-      wd &= wd - 1;
-      sorted[2 * rank] = pos;                       // .x of group `rank`
-      if (rank > 0) sorted[2 * rank - 1] = pos;     // .y of the group before it
-      rank++;
-    }
-  }
-  // the last group ends at n: written by whoever holds the last word
-  if (w0 <= nwords - 1 && nwords - 1 < w0 + 4) sorted[2 * rank - 1 + 0] = n;
 }
 
 // ---- K7: monopoles (Octree::ComputeMass, OctreeSearch.h:83-97) ---------------------------------------------------
@@ -750,305 +688,6 @@ bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__
     for (int k = 0; k < B; k++) {
       const int i = r.x + lane + 32 * k;
       if (i < r.y && i >= t0 && i < t1) {
-        float4 a = make_float4(G * (ax[k].x + ax[k].y), G * (ay[k].x + ay[k].y), G * (az[k].x + az[k].y), 0.f);
-        if (accumulate) { const float4 o = acc[i]; a.x += o.x; a.y += o.y; a.z += o.z; }
-        acc[i] = a;
-      }
-    }
-  }
-  if (lane == 0 && inter) atomicAdd(&c->interactions, inter);
-}
-
-// ---- K8a-S: one traversal shared by S neighbouring walk groups -------------------------------------------------
-// A warp takes S consecutive walk groups of the Morton order (<= 32 bodies each; body k of a lane belongs to group k) and
-// walks the tree ONCE for all of them: every stack entry carries the set of groups that still need the cell; a popped
-// cell is tested against each of those groups' boxes with the same criterion as above - accepted for some (it joins
-// THEIR interaction rings), opened for the rest (children are pushed with that set; bodies of an opened leaf go to the
-// rings of that set). Each group therefore evaluates exactly the interactions the single-group walk gives it (the order in
-// which they arrive can differ, so results agree to rounding, not bit for bit), while the traversal (most of the walk's
-// instructions and all of its latency) is paid once per S groups, and the evaluation runs S independent streams side by
-// side (ring k against body slot k). Which groups share a warp depends only on the tree, not on the target range
-// [t0, t1): a warp whose groups straddle the range walks for all of them and writes only the bodies inside it, so a
-// rank of the replicated-tree mode computes bit for bit what a single GPU computes.
-// The rings advance in lock step: n entries are flushed from all of them when every ring holds n >= 32; if one ring is
-// about to overflow while another is nearly empty, the short ones are padded with massless entries.
-constexpr int kShareCap = 128;           // ring entries per group
-constexpr int kShareNodeMask = (1 << 28) - 1;
-
-template <int S, bool EPS0>
-__device__ __forceinline__ void eval_share(const float* __restrict__ ring, const int (&head)[S], const unsigned act, const int count,
-                                           const float2 (&nx)[S], const float2 (&ny)[S], const float2 (&nz)[S], const float2 eps2,
-                                           float2 (&ax)[S], float2 (&ay)[S], float2 (&az)[S]) {
-  // `count` entries (a multiple of 4) of every ring in `act` (warp-uniform), each from its own head
-#pragma unroll 2
-  for (int j = 0; j < count; j += 4) {
-#pragma unroll
-    for (int k = 0; k < S; k++) {
-      if (!((act >> k) & 1u)) continue;
-      const float* r = ring + k * 4 * kShareCap + ((head[k] + j) & (kShareCap - 1));
-      const float4 X = *reinterpret_cast<const float4*>(r);
-      const float4 Y = *reinterpret_cast<const float4*>(r + kShareCap);
-      const float4 Z = *reinterpret_cast<const float4*>(r + 2 * kShareCap);
-      const float4 M = *reinterpret_cast<const float4*>(r + 3 * kShareCap);
-      interact2<EPS0>(f2(X.x, X.y), f2(Y.x, Y.y), f2(Z.x, Z.y), f2(M.x, M.y), nx[k], ny[k], nz[k], eps2, ax[k], ay[k], az[k]);
-      interact2<EPS0>(f2(X.z, X.w), f2(Y.z, Y.w), f2(Z.z, Z.w), f2(M.z, M.w), nx[k], ny[k], nz[k], eps2, ax[k], ay[k], az[k]);
-    }
-  }
-}
-
-template <int S>
-struct ShareSmem {
-  float ring[kWalkWarps][S * 4 * kShareCap];
-  float box[kWalkWarps][S][8];              // per group: centre xyz, -, half extents xyz, -
-  int stk[kWalkWarps][kStackWin];
-  int offs[kWalkWarps][32];
-};
-
-template <int S, bool EPS0>
-__global__ void __launch_bounds__(kWalkThreads, S <= 2 ? 3 : 2)
-bh_walk_share_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com, const int4* __restrict__ node_meta,
-                     const float4* __restrict__ tgt, const int2* __restrict__ groups, Counters* __restrict__ c,
-                     const float4* __restrict__ root, const float theta2, const float eps2, const float G, const int t0,
-                     const int t1, const int accumulate, int* __restrict__ stacks, float4* __restrict__ acc,
-                     int* __restrict__ group_cost, uint32_t* __restrict__ bin_cost, const int n_targets) {
-  extern __shared__ __align__(16) unsigned char share_raw[];
-  ShareSmem<S>& sm = *reinterpret_cast<ShareSmem<S>*>(share_raw);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* ring = sm.ring[w];
-  float (*sbox)[8] = sm.box[w];
-  int* stk = sm.stk[w];
-  int* offs = sm.offs[w];
-  int* gstack = stacks + (size_t)(blockIdx.x * kWalkWarps + w) * kStackCap;
-  const int ngroups = c->ngroups;
-  const int nsuper = (ngroups + S - 1) / S;
-  const float root_half = root[0].w;
-  const unsigned lt = (1u << lane) - 1u;
-  const float2 eps2v = f2(eps2, eps2);
-  unsigned long long inter = 0;
-  for (int j = lane; j < S * 4 * kShareCap; j += 32) ring[j] = 0.f;   // stale ring entries must at least be finite
-  __syncwarp();
-  while (true) {
-    int sg = 0;
-    if (lane == 0) sg = atomicAdd(&c->next_group, 1);
-    sg = __shfl_sync(0xffffffffu, sg, 0);
-    if (sg >= nsuper) break;
-    int2 r[S];
-    unsigned vmask = 0;
-    bool wanted = false;
-#pragma unroll
-    for (int k = 0; k < S; k++) {
-      const int g = sg * S + k;
-      r[k] = g < ngroups ? groups[g] : make_int2(0, 0);
-      if (g < ngroups) vmask |= 1u << k;
-      wanted = wanted || min(r[k].y, t1) - max(r[k].x, t0) > 0;
-    }
-    if (!wanted) continue;
-    const int kfirst = __ffs(vmask) - 1;
-    int first_body = r[0].x;
-#pragma unroll
-    for (int k = 0; k < S; k++) if (k == kfirst) first_body = r[k].x;
-    float2 nx[S], ny[S], nz[S], ax[S], ay[S], az[S];
-#pragma unroll
-    for (int k = 0; k < S; k++) {
-      ax[k] = f2(0.f, 0.f); ay[k] = f2(0.f, 0.f); az[k] = f2(0.f, 0.f);
-      const bool valid = (vmask >> k) & 1u;
-      const int i = r[k].x + lane;
-      const float4 p = tgt[valid ? (i < r[k].y ? i : r[k].x) : first_body];
-      nx[k] = f2(-p.x, -p.x); ny[k] = f2(-p.y, -p.y); nz[k] = f2(-p.z, -p.z);
-      float lox = p.x, loy = p.y, loz = p.z, hix = p.x, hiy = p.y, hiz = p.z;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
-        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
-        loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
-      }
-      if (lane == 0) {
-        sbox[k][0] = 0.5f * (lox + hix); sbox[k][1] = 0.5f * (loy + hiy); sbox[k][2] = 0.5f * (loz + hiz); sbox[k][3] = 0.f;
-        sbox[k][4] = 0.5f * (hix - lox); sbox[k][5] = 0.5f * (hiy - loy); sbox[k][6] = 0.5f * (hiz - loz); sbox[k][7] = 0.f;
-      }
-    }
-    int pend[S];
-    unsigned ent[S];
-#pragma unroll
-    for (int k = 0; k < S; k++) { pend[k] = 0; ent[k] = 0; }
-    int head[S];
-#pragma unroll
-    for (int k = 0; k < S; k++) head[k] = 0;
-    int top = 1, base = 0;
-    int leaf_first = 0, leaf_excl = 0, ltotal = 0, lpos = 0;
-    unsigned leaf_mask = 0;
-    if (lane == 0) stk[0] = (int)(vmask << 28);   // the root, needed by every group
-    __syncwarp();
-    bool overflow = false;
-    // entry v of group k goes to slot (head[k] + pos) of ring k
-    auto put = [&](const int k, const int pos, const float4 v) {
-      float* d = ring + k * 4 * kShareCap + ((head[k] + pos) & (kShareCap - 1));
-      d[0] = v.x; d[kShareCap] = v.y; d[2 * kShareCap] = v.z; d[3 * kShareCap] = v.w;
-    };
-    // every ring that holds kFlush entries evaluates them (rings that do so in the same trip run side by side); no padding
-    auto flush_if_needed = [&]() {
-      unsigned act = 0;
-#pragma unroll
-      for (int k = 0; k < S; k++) if (pend[k] >= kFlush) act |= 1u << k;
-      if (!act) return;
-      eval_share<S, EPS0>(ring, head, act, kFlush, nx, ny, nz, eps2v, ax, ay, az);
-#pragma unroll
-      for (int k = 0; k < S; k++) if ((act >> k) & 1u) { head[k] = (head[k] + kFlush) & (kShareCap - 1); pend[k] -= kFlush; }
-      __syncwarp();
-    };
-    // 32 bodies (lane < cnt holds one) join the rings of the groups in `mask`
-    auto add_bodies = [&](const bool have, const float4 bd, const unsigned mask) {
-#pragma unroll
-      for (int k = 0; k < S; k++) {
-        const bool mine = have && ((mask >> k) & 1u);
-        const unsigned bal = __ballot_sync(0xffffffffu, mine);
-        if (mine) put(k, pend[k] + __popc(bal & lt), bd);
-        pend[k] += __popc(bal);
-        ent[k] += __popc(bal);
-      }
-    };
-    while (true) {
-      if (lpos < ltotal) {
-        const int j = lpos + lane;
-        int L = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) if (offs[L + step] <= j) L += step;
-        const int first = __shfl_sync(0xffffffffu, leaf_first, L), off = __shfl_sync(0xffffffffu, leaf_excl, L);
-        const unsigned lm = __shfl_sync(0xffffffffu, leaf_mask, L);
-        const bool have = j < ltotal;
-        float4 bd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (have) bd = posm[first + (j - off)];
-        add_bodies(have, bd, lm);
-        lpos += 32;
-      } else if (top + base > 0) {
-        if (top == 0) {
-          const int cnt = min(base, kStackWin / 2);
-          for (int k = lane; k < cnt; k += 32) stk[k] = gstack[base - cnt + k];
-          base -= cnt;
-          top = cnt;
-          __syncwarp();
-        }
-        const int nb = min(32, top);
-        top -= nb;
-        const int e = lane < nb ? stk[top + lane] : -1;
-        float4 item = make_float4(0.f, 0.f, 0.f, 0.f);
-        unsigned acc_set = 0, open_set = 0;
-        int push_first = 0, push_n = 0, leaf_n = 0;
-        leaf_first = 0;
-        leaf_mask = 0;
-        if (lane < nb) {
-          const int cell = e & kShareNodeMask;
-          const unsigned need = (unsigned)e >> 28;
-          const float4 cm = node_com[cell];
-          const int4 m = node_meta[cell];
-          const bool leaf = (m.z & kLeafFlag) != 0;
-          const float size = root_half * __int_as_float((127 - (m.z & 255)) << 23);
-          const float size2 = size * size;
-          unsigned ok = 0;
-#pragma unroll
-          for (int k = 0; k < S; k++) {
-            const float4 bc = *reinterpret_cast<const float4*>(sbox[k]), bh = *reinterpret_cast<const float4*>(sbox[k] + 4);
-            const float dx = fmaxf(fabsf(cm.x - bc.x) - bh.x, 0.f), dy = fmaxf(fabsf(cm.y - bc.y) - bh.y, 0.f),
-                        dz = fmaxf(fabsf(cm.z - bc.z) - bh.z, 0.f);
-            if (size2 < theta2 * (dx * dx + dy * dy + dz * dz)) ok |= 1u << k;
-          }
-          if (leaf && m.y == 1) ok = need;
-          acc_set = need & ok;
-          open_set = need & ~ok;
-          item = cm;
-          if (open_set) {
-            if (leaf) { leaf_first = m.x; leaf_n = m.y; leaf_mask = open_set; }
-            else { push_first = m.x; push_n = m.y; }
-          }
-        }
-        // a leaf too large for the packed scan below (a deepest-level cell full of coincident bodies): stream it on its own
-        unsigned big = __ballot_sync(0xffffffffu, leaf_n >= kLeafChunk);
-        while (big) {
-          const int src = __ffs(big) - 1;
-          big &= big - 1;
-          const int f = __shfl_sync(0xffffffffu, leaf_first, src), n = __shfl_sync(0xffffffffu, leaf_n, src);
-          const unsigned lm = __shfl_sync(0xffffffffu, leaf_mask, src);
-          for (int b0 = 0; b0 < n; b0 += 32) {
-            const bool have = b0 + lane < n;
-            float4 bd = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (have) bd = posm[f + b0 + lane];
-            add_bodies(have, bd, lm);
-            __syncwarp();
-            flush_if_needed();
-          }
-          if (lane == src) leaf_n = 0;
-        }
-        int incl = push_n | (leaf_n << 10);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int both = __shfl_sync(0xffffffffu, incl, 31);
-        const int total = both & 1023;
-        ltotal = both >> 10;
-        lpos = 0;
-        leaf_excl = (incl >> 10) - leaf_n;
-        if (ltotal) offs[lane] = leaf_excl;
-        if (total) {
-          if (top + total > kStackWin) {
-            const int sp = min(top, max(kStackWin / 2, top + total - kStackWin));
-            if (base + sp > kStackCap) { overflow = true; break; }
-            for (int k = lane; k < sp; k += 32) gstack[base + k] = stk[k];
-            base += sp;
-            __syncwarp();
-            for (int k0 = 0; k0 < top - sp; k0 += 32) {
-              const int v = k0 + lane < top - sp ? stk[sp + k0 + lane] : 0;
-              __syncwarp();
-              if (k0 + lane < top - sp) stk[k0 + lane] = v;
-            }
-            top -= sp;
-            __syncwarp();
-          }
-          int* dst = stk + top + (incl & 1023) - push_n;
-          const int tagged = push_first | (int)(open_set << 28);
-#pragma unroll
-          for (int k = 0; k < 8; k++) if (k < push_n) dst[k] = tagged + k;
-          top += total;
-        }
-        // accepted cells join the rings of the groups that accepted them
-#pragma unroll
-        for (int k = 0; k < S; k++) {
-          const bool mine = (acc_set >> k) & 1u;
-          const unsigned bal = __ballot_sync(0xffffffffu, mine);
-          if (mine) put(k, pend[k] + __popc(bal & lt), item);
-          pend[k] += __popc(bal);
-          ent[k] += __popc(bal);
-        }
-      } else {
-        break;
-      }
-      __syncwarp();
-      flush_if_needed();
-    }
-    if (overflow && lane == 0) atomicExch(&c->overflow, 1);
-    if (!overflow) {   // what is left: every ring padded with massless entries to the longest one's length (rounded up to 4)
-      int mx = 0;
-      unsigned act = 0;
-#pragma unroll
-      for (int k = 0; k < S; k++) if (pend[k] > 0) { mx = max(mx, pend[k]); act |= 1u << k; }
-      const int n = (mx + 3) & ~3;
-#pragma unroll
-      for (int k = 0; k < S; k++)
-        if ((act >> k) & 1u)
-          for (int j = pend[k] + lane; j < n; j += 32) ring[k * 4 * kShareCap + 3 * kShareCap + ((head[k] + j) & (kShareCap - 1))] = 0.f;
-      __syncwarp();
-      if (act) eval_share<S, EPS0>(ring, head, act, n, nx, ny, nz, eps2v, ax, ay, az);
-      __syncwarp();
-    }
-#pragma unroll
-    for (int k = 0; k < S; k++) {
-      if (!((vmask >> k) & 1u)) continue;
-      const int g = sg * S + k;
-      const unsigned long long work = (unsigned long long)ent[k] * (unsigned long long)max(min(r[k].y, t1) - max(r[k].x, t0), 0);
-      inter += work;
-      if (group_cost && lane == 0) group_cost[g] = (accumulate ? group_cost[g] : 0) + (int)min(ent[k], 0x3fffffffu);
-      if (bin_cost && lane == 0 && work)
-        atomicAdd(bin_cost + min((int)((long long)r[k].x * kCostBins / max(n_targets, 1)), kCostBins - 1), (uint32_t)min(work, 0xffffffffull));
-      const int i = r[k].x + lane;
-      if (i < r[k].y && i >= t0 && i < t1) {
         float4 a = make_float4(G * (ax[k].x + ax[k].y), G * (ay[k].x + ay[k].y), G * (az[k].x + az[k].y), 0.f);
         if (accumulate) { const float4 o = acc[i]; a.x += o.x; a.y += o.y; a.z += o.z; }
         acc[i] = a;
@@ -1437,20 +1076,12 @@ __global__ void iota_kernel(int32_t* ids, int n, int first) {
 template <int B, bool EPS0>
 int launch_walk(Impl* m, Impl* g, const BHParams& p, const float4* posm, const float4* tgt, float4* acc, int t0, int t1,
                 bool accumulate, cudaStream_t s) {
-  // 0 = one warp per walk group traverses and evaluates; 1 = warp-specialised (profiles/r2_walk_warp_specialised.md);
-  // 2 = one traversal shared by `share` neighbouring 32-body groups per warp
-  static const int mode_env = getenv("NBODY_WALK") ? atoi(getenv("NBODY_WALK")) : 2;
+  // 0 = one warp per walk group traverses and evaluates (default); 1 = warp-specialised (profiles/r2_walk_warp_specialised.md)
+  static const int mode = getenv("NBODY_WALK") ? atoi(getenv("NBODY_WALK")) : 0;
   static const int split = getenv("NBODY_WS_SPLIT") ? atoi(getenv("NBODY_WS_SPLIT")) : 2;   // register split: 0 = 64/64, 1 = 40/88, 2 = 48/80
-  static const int share = getenv("NBODY_WALK_SHARE") ? atoi(getenv("NBODY_WALK_SHARE")) : 4;
-  const int mode = (mode_env == 2 && B != 1) ? 0 : mode_env;
   auto ws = split == 1 ? bh_walk_ws_kernel<B, EPS0, (B <= 2 ? 1 : 0)> : split == 2 ? bh_walk_ws_kernel<B, EPS0, (B <= 2 ? 2 : 0)> : bh_walk_ws_kernel<B, EPS0, 0>;
-  auto sh = share == 2 ? bh_walk_share_kernel<2, EPS0> : bh_walk_share_kernel<4, EPS0>;
-  const size_t sh_smem = share == 2 ? sizeof(ShareSmem<2>) : sizeof(ShareSmem<4>);
   int per_sm = 0;
-  if (mode == 2) {
-    NB_CUDA(cudaFuncSetAttribute(sh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_smem));
-    NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sh, kWalkThreads, sh_smem));
-  } else if (mode == 1) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ws, kWsThreads, 0));
+  if (mode == 1) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ws, kWsThreads, 0));
   else NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_walk_group_kernel<B, EPS0>, kWalkThreads, 0));
   const int grid = sm_count() * std::max(1, std::min(per_sm, 8));
   const int64_t need = (int64_t)grid * (mode == 1 ? kWsPairs : kWalkWarps) * kStackCap;
@@ -1460,10 +1091,7 @@ int launch_walk(Impl* m, Impl* g, const BHParams& p, const float4* posm, const f
     m->cap_stacks = need;
   }
   NB_CUDA(cudaMemsetAsync(&g->counters->next_group, 0, sizeof(int), s));
-  if (mode == 2)
-    sh<<<grid, kWalkThreads, sh_smem, s>>>(posm, m->node_com, m->node_meta, tgt, g->groups_sorted, g->counters, m->root, p.theta * p.theta, p.eps2, p.G,
-                                           t0, t1, accumulate ? 1 : 0, m->stacks, acc, g->group_cost, g->bin_cost, g->n);
-  else if (mode == 1)
+  if (mode == 1)
     ws<<<grid, kWsThreads, 0, s>>>(posm, m->node_com, m->node_meta, tgt, g->groups, g->counters, m->root, p.theta * p.theta, p.eps2, p.G, t0, t1,
                                    accumulate ? 1 : 0, m->stacks, acc, g->group_cost, g->bin_cost, g->n);
   else
@@ -1491,7 +1119,7 @@ void bh_free(BHState& st) {
   Impl* m = static_cast<Impl*>(st.impl);
   for (int k = 0; k < 2; k++) { cudaFree(m->sort.keys[k]); cudaFree(m->sort.idx[k]); }
   cudaFree(m->sort.work);
-  cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->node_bmin); cudaFree(m->node_bmax); cudaFree(m->groups); cudaFree(m->groups_sorted); cudaFree(m->group_bits); cudaFree(m->group_cost);
+  cudaFree(m->node_com); cudaFree(m->node_meta); cudaFree(m->node_range); cudaFree(m->node_ready); cudaFree(m->node_bmin); cudaFree(m->node_bmax); cudaFree(m->groups); cudaFree(m->group_cost);
   cudaFree(m->counters); cudaFree(m->root); cudaFree(m->stacks); cudaFree(m->boxes);
   cudaFree(m->samples); cudaFree(m->splitters); cudaFree(m->send_off); cudaFree(m->all_off); cudaFree(m->peer_pub); cudaFree(m->pub_node);
   cudaFree(m->visit); cudaFree(m->let_out); cudaFree(m->bin_cost); cudaFree(m->ret); if (m->h_counts) cudaFreeHost(m->h_counts); if (m->ev_counts) cudaEventDestroy(m->ev_counts); cudaFree(m->let_in); cudaFree(m->let_sorted); cudaFree(m->all_pos);
@@ -1532,13 +1160,11 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
   if (p.group_size != 32 && p.group_size != 64 && p.group_size != 128) { set_error("Barnes-Hut: group_size must be 32, 64 or 128"); return -1; }
   m->built_group_size = p.group_size;
   const int super = p.group_size * std::max(1, p.group_pack);
-  const int gwords = n / 32 + 1;
-  NB_CUDA(cudaMemsetAsync(m->group_bits, 0, (size_t)gwords * 4, s));
-  tree_init_kernel<<<1, 1, 0, s>>>(keys, n, p.group_size, super, m->node_range, m->node_meta, m->node_ready, m->groups, m->group_bits, m->counters);
+  tree_init_kernel<<<1, 1, 0, s>>>(keys, n, p.group_size, super, m->node_range, m->node_meta, m->node_ready, m->groups, m->counters);
   *launches += 2;
   {
     int leaf = std::max(1, p.leaf_size), gs = p.group_size, sup = super, lv = levels;
-    void* args[] = {(void*)&keys, &leaf, &gs, &sup, &lv, &m->node_range, &m->node_meta, &m->node_ready, &m->groups, &m->group_bits, &m->counters};
+    void* args[] = {(void*)&keys, &leaf, &gs, &sup, &lv, &m->node_range, &m->node_meta, &m->node_ready, &m->groups, &m->counters};
     // as many CTAs as are co-resident (the split is latency bound: dependent key probes), 1 per SM when another
     // stream's walk shares the SMs
     static int split_ctas = 0;
@@ -1547,13 +1173,6 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
       split_ctas = std::max(1, std::min(split_ctas, 8));
     }
     NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(sm_count() * split_ctas), dim3(256), args, 0, s));
-  }
-  {  // the walk groups in Morton order (for the walk that shares one traversal between neighbouring groups)
-    const int nblk = (gwords + kBitsPerBlock - 1) / kBitsPerBlock;
-    uint32_t* block_sums = m->group_bits + m->cap_group_bits;
-    group_bits_count_kernel<<<nblk, 256, 0, s>>>(m->group_bits, gwords, block_sums);
-    group_sort_kernel<<<nblk, 256, 0, s>>>(m->group_bits, gwords, block_sums, n, reinterpret_cast<int*>(m->groups_sorted));
-    *launches += 2;
   }
   if (p.node_boxes) {
     if (m->cap_boxes_nodes < m->cap_nodes) {

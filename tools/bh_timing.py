@@ -16,7 +16,7 @@ for n in sizes:
     print(f"N={n}: radix sort 63-bit pairs {ms:.3f} ms = {n / ms * 1e-6:.2f} Gkeys/s = {n * 24 * 8 / ms * 1e-6:.0f} GB/s of (12 r + 12 w) x 8 passes")
     combos = [(64, 2, 16)]
     if len(sys.argv) > 2 and sys.argv[2] == "walk":   # the two walk-group shapes that matter, for kernel A/B runs (NBODY_WALK=0/1)
-        combos = [(32, 2, 16), (32, 2, 8), (32, 1, 16), (32, 4, 16)] if os.environ.get("NBODY_WALK", "2") == "2" else [(32, 2, 16), (64, 2, 16)]
+        combos = [(32, 2, 16), (64, 2, 16), (64, 2, 8), (128, 2, 16)]
     if sweep:
         combos = [(gs, pack, leaf) for gs in (32, 64) for pack in (1, 2, 4) for leaf in (8, 16, 32)]
     for th in ((0.25,) if sweep else (0.25, 0.35)):
