@@ -352,15 +352,21 @@ def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_basel
     e2e_steps = max(1, min(steps, args.e2e_steps if method == "direct" else max(args.e2e_steps, 20)))
     barrier()
     e0 = time.perf_counter()
+    e2e_parts = [0.0, 0.0, 0.0]   # host-clock time inside the three calls of an iteration (each returns synchronised)
     for _ in range(e2e_steps):
         t_it = time.perf_counter()
         sim.SetParticlesRaw(aos_in.data_ptr(), n, 40)     # H2D: this rank's FParticle records
+        t_a = time.perf_counter()
         sim.Tick()                                        # OctreeSearch.cpp:21-34
+        t_b = time.perf_counter()
         sim.GetParticlesRaw(aos_out.data_ptr(), n, 40)    # D2H: this rank's FParticle records
+        t_c = time.perf_counter()
+        e2e_parts[0] += t_a - t_it; e2e_parts[1] += t_b - t_a; e2e_parts[2] += t_c - t_b
         if os.environ.get("NBODY_BENCH_TRACE"):
             print(f"[bench rank {rank}] e2e iteration {1e3 * (time.perf_counter() - t_it):.2f} ms", file=sys.stderr)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - e0)
+    e2e_parts = [max_over_ranks(x) * 1e3 / e2e_steps for x in e2e_parts]
     stats = sim.Stats()
     sim.close()
 
@@ -425,7 +431,8 @@ def run_workload(args, name, ctx, steps, warmup, min_seconds=0.0, with_cpu_basel
         "e2e": {"value": e2e_value, "unit": unit,
                 "h2d_bytes_per_step": int(n) * 40 * (world if (method == "bh" and world > 1 and not lets) else 1),
                 "d2h_bytes_per_step": int(n) * 40,
-                "steps": e2e_steps, "api": "OctreeSearch.Particles <- pinned FParticle AoS; Tick(); Particles -> pinned AoS"},
+                "steps": e2e_steps, "api": "OctreeSearch.Particles <- pinned FParticle AoS; Tick(); Particles -> pinned AoS",
+                "ms_per_call_max_over_ranks": {"set_particles": e2e_parts[0], "tick": e2e_parts[1], "get_particles": e2e_parts[2]}},
         "gpu_launches": int(launches),
         "roofline": roof,
     }
