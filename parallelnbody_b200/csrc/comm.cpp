@@ -110,11 +110,16 @@ class NcclComm : public Comm {
   }
   int all_to_all_v(const void* send, const size_t* send_bytes, const size_t* send_off, void* recv, const size_t* recv_bytes,
                    const size_t* recv_off, cudaStream_t s) override {
+    // what a rank keeps for itself is a plain device copy (HBM speed), not a send / receive pair through NCCL's channels
+    if (send_bytes[rank_] && send_bytes[rank_] == recv_bytes[rank_] && (const char*)send + send_off[rank_] != (char*)recv + recv_off[rank_])
+      NB_CUDA(cudaMemcpyAsync((char*)recv + recv_off[rank_], (const char*)send + send_off[rank_], send_bytes[rank_], cudaMemcpyDeviceToDevice, s));
+    const bool self_done = send_bytes[rank_] == recv_bytes[rank_];
     NB_NCCL(api()->GroupStart(), "ncclGroupStart");
     // an error inside the group must still close it, or every later NCCL call of this thread joins the open group
     ncclResult_t bad = ncclSuccess;
     const char* where = "";
     for (int p = 0; p < world_ && bad == ncclSuccess; p++) {
+      if (p == rank_ && self_done) continue;
       if (send_bytes[p]) { bad = api()->Send((const char*)send + send_off[p], send_bytes[p], ncclInt8, p, comm_, s); where = "ncclSend"; }
       if (bad == ncclSuccess && recv_bytes[p]) { bad = api()->Recv((char*)recv + recv_off[p], recv_bytes[p], ncclInt8, p, comm_, s); where = "ncclRecv"; }
     }
@@ -126,11 +131,17 @@ class NcclComm : public Comm {
 
   int all_to_all_v_multi(int nbuf, const void* const* send, void* const* recv, const size_t* elem, const size_t* send_cnt,
                          const size_t* send_off, const size_t* recv_cnt, const size_t* recv_off, cudaStream_t s) override {
+    const bool self_done = send_cnt[rank_] == recv_cnt[rank_];
+    if (self_done && send_cnt[rank_])
+      for (int k = 0; k < nbuf; k++)
+        NB_CUDA(cudaMemcpyAsync((char*)recv[k] + recv_off[rank_] * elem[k], (const char*)send[k] + send_off[rank_] * elem[k], send_cnt[rank_] * elem[k],
+                                cudaMemcpyDeviceToDevice, s));
     NB_NCCL(api()->GroupStart(), "ncclGroupStart");
     ncclResult_t bad = ncclSuccess;
     const char* where = "";
     for (int k = 0; k < nbuf && bad == ncclSuccess; k++)
       for (int p = 0; p < world_ && bad == ncclSuccess; p++) {
+        if (p == rank_ && self_done) continue;
         if (send_cnt[p]) { bad = api()->Send((const char*)send[k] + send_off[p] * elem[k], send_cnt[p] * elem[k], ncclInt8, p, comm_, s); where = "ncclSend"; }
         if (bad == ncclSuccess && recv_cnt[p]) { bad = api()->Recv((char*)recv[k] + recv_off[p] * elem[k], recv_cnt[p] * elem[k], ncclInt8, p, comm_, s); where = "ncclRecv"; }
       }
