@@ -1,23 +1,22 @@
 #!/bin/bash
-# usage: gpurun --gpus N -- 'bash tools/gpu_multi.sh <tag> N [workloads...]'
-tag=${1:-m}; N=${2:-2}; shift; shift
-WL=${@:-plummer_1m_direct plummer_1m_bh}
+# Round 2 multi-GPU call: NCCL parity check, the default bench line (direct + bh object) and the reference arm under torchrun.
+# usage: gpurun --gpus N --timeout 1500 -- 'bash tools/gpu_multi.sh N tag'
+N=${1:-2}; tag=${2:-r2m}
 out=gpurun_out; mkdir -p $out
-nvidia-smi --query-gpu=index,name --format=csv,noheader | head -2
-timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu --timeout 600 > $out/pytest_multi_$tag.log 2>&1; echo "pytest rc=$?"
-tail -12 $out/pytest_multi_$tag.log
-for wl in $WL; do
-for n in 1 $N; do
-  f=$out/bench_${wl}_g${n}_$tag
-  if [ $n = 1 ]; then timeout 900 python bench.py --gpus 1 --workload $wl --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $f.json 2> $f.err
-  else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $n --workload $wl --steps 5 --warmup 3 --e2e-steps 1 > $f.json 2> $f.err; fi
-  echo "bench $wl gpus=$n rc=$?"; python - <<PY
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29611 tools/multi_gpu_check.py > $out/multi_gpu_check_${N}gpu_$tag.log 2>&1; echo "multi check rc=$?"
+grep -E "method=|MULTI-GPU|Error|error" $out/multi_gpu_check_${N}gpu_$tag.log | tail -8
+timeout 900 $TR --master-port 29612 bench.py --gpus $N --steps 10 --warmup 3 > $out/bench_${N}gpu_$tag.json 2> $out/bench_${N}gpu_$tag.err; echo "bench rc=$?"
+python - <<PY
 import json
 try:
-    d=json.loads(open("$f.json").read().strip().splitlines()[-1])
-    print({k:d[k] for k in ("value","unit","n_gpus","ms_per_step","phases_ms_per_step")}, "e2e", d["e2e"]["value"])
+    d=json.loads(open('$out/bench_${N}gpu_$tag.json').read().strip().splitlines()[-1])
+    print('direct', d['value'], 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'])
+    b=d.get('bh')
+    if b: print('bh', b['config']['name'], b['value'], 'steps/s e2e', b['e2e']['value'], 'ms', b['ms_per_step'], b['phases_ms_per_step_max_over_ranks'], 'let', b['let_points_max'], 'bodies', b['bodies_per_rank'], 'clk', b['clocks'])
 except Exception as e:
-    print("no json", e); print(open("$f.err").read()[-1500:])
+    print('parse failed', e)
 PY
-done
-done
+tail -5 $out/bench_${N}gpu_$tag.err
+timeout 600 $TR --master-port 29613 bench.py --impl reference --gpus $N --steps 3 --warmup 1 --no-extras > $out/bench_ref_${N}gpu_$tag.json 2>> $out/bench_${N}gpu_$tag.err; echo "ref rc=$?"
+cut -c1-400 $out/bench_ref_${N}gpu_$tag.json
