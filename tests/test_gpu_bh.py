@@ -401,3 +401,37 @@ def test_config5_two_galaxies_16m_theta07_one_gpu():
         assert len(ids) == 16384
         errs.append(rel_l2(acc[ids], exact))
     assert max(errs) <= 1.4e-2, f"theta 0.35 at 16M: {errs}"
+
+
+# ------------------------------------------------------------------------------ the warp-specialised walk (NBODY_WALK=1)
+_WS_SNIPPET = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import parallelnbody_b200 as P
+from parallelnbody_b200 import ic
+posm, vel = ic.plummer(30011, seed=7)
+out = []
+for gs, eps in ((32, 0.01), (64, 0.0)):
+    with P.OctreeSearch(method=P.METHOD_BARNES_HUT, eps=eps, theta=0.3, group_size=gs) as s:
+        s.SetBodies(posm, vel)
+        s.CreateOctree()
+        out.append(s.Accelerations())
+np.save({path!r}, np.stack(out))
+"""
+
+
+def test_warp_specialised_walk_is_bit_identical_to_the_default(tmp_path):
+    """The producer / consumer variant of the walk (traversing and evaluating warps, mbarrier hand-off) is kept as a
+    measured experiment behind NBODY_WALK=1; one producer feeds one consumer in order, so it must reproduce the default
+    kernel bit for bit. The switch is read once per process, hence the two interpreter runs."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for mode in ("0", "1"):
+        path = str(tmp_path / f"acc_walk{mode}.npy")
+        env = dict(os.environ, NBODY_WALK=mode)
+        subprocess.run([sys.executable, "-c", _WS_SNIPPET.format(root=root, path=path)], check=True, env=env, timeout=300)
+        res.append(np.load(path))
+    assert np.isfinite(res[0]).all() and np.abs(res[0][..., :3]).max() > 0
+    assert np.array_equal(res[0], res[1])
