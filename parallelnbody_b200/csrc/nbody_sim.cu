@@ -351,11 +351,13 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       // synchronisation), (3) LET exchange + tree beside the local walk, then the walk over the received points,
       // (4) kick-drift, new splitters, lazy migration; see bh.cu K9
       // NBODY_LET_TRACE=1: synchronise after every phase and print host-clock phase times (development aid)
-      static const bool trace = getenv("NBODY_LET_TRACE") != nullptr;
+      // NBODY_LET_TRACE=2: no synchronisation, host-clock time at which each phase has been ENQUEUED (is the host ahead of the GPU?)
+      static const int trace = getenv("NBODY_LET_TRACE") ? std::max(1, atoi(getenv("NBODY_LET_TRACE"))) : 0;
       auto t_prev = std::chrono::steady_clock::now();
       auto lap = [&](const char* what) {
         if (!trace) return;
-        cudaStreamSynchronize(s->stream);
+        if (trace == 1) cudaStreamSynchronize(s->stream);
+        else if (s->steps % 50 != 7) return;
         const auto now = std::chrono::steady_clock::now();
         fprintf(stderr, "[let rank %d step %lld] %-14s %8.3f ms  n_local=%lld n_let=%d\n", s->cfg.rank, (long long)s->steps, what,
                 std::chrono::duration<double, std::milli>(now - t_prev).count(), (long long)s->n_local, s->n_let);
@@ -403,6 +405,7 @@ int enqueue_step(nbody_sim* s, float dt, bool integrate, cudaEvent_t* ev) {
       phase(3);
       NB_TRY(bh_forces(s->tree, bp, s->d_posm, s->d_acc, (int)s->n_local, 0, (int)s->n_local, s->stream, &launches));
       phase(4);
+      if (trace == 2) lap("walk enqueued");
       NB_TRY(bh_let_plan_wait(s->tree, cap, &plan));
       lap("walk local");
       NB_TRY(bh_let_import(s->tree, s->tree_let, s->comm, bp, plan, s->d_box, &s->n_let, s->stream, &launches));
