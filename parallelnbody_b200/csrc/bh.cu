@@ -36,6 +36,7 @@ constexpr int kLeafFlag = 1 << 8;
 // walk groups hold <= group_size bodies (32 * B, B bodies per lane, B in {1, 2, 4})
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
+constexpr int kWalkMinCtas1 = 4;         // one body per lane: 64 registers -> 32 warps per SM
 constexpr int kWalkMinCtas = 3;          // register budget: 80 per thread -> 24 warps per SM (64 registers spill the streamed-leaf walk)
 constexpr int kStackCap = 8192;          // per-warp spill slab of the walk stack (HBM/L2 resident; cells only, rarely touched)
 constexpr int kStackSmem = 512;          // per-warp stack window in shared memory
@@ -491,7 +492,7 @@ __device__ __forceinline__ void eval_list(const float* __restrict__ ring, const 
 }
 
 template <int B, bool EPS0>
-__global__ void __launch_bounds__(kWalkThreads, B <= 2 ? kWalkMinCtas : 2)
+__global__ void __launch_bounds__(kWalkThreads, B == 1 ? kWalkMinCtas1 : B == 2 ? kWalkMinCtas : 2)
 bh_walk_group_kernel(const float4* __restrict__ posm, const float4* __restrict__ node_com, const int4* __restrict__ node_meta,
                      const float4* __restrict__ tgt, const int2* __restrict__ groups, Counters* __restrict__ c,
                      const float4* __restrict__ root, const float theta2, const float eps2, const float G, const int t0,
