@@ -36,7 +36,7 @@ constexpr int kLeafFlag = 1 << 8;
 // walk groups hold <= group_size bodies (32 * B, B bodies per lane, B in {1, 2, 4})
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
-constexpr int kWalkMinCtas1 = 3;         // one body per lane: 4 CTAs (64 registers, 32 warps per SM) measured 4 % slower than 3
+constexpr int kWalkMinCtas1 = 3;         // one body per lane: measured 2.19 ms at 3 CTAs per SM, 2.28 at 4 (64 registers), 2.45 at 2 (100 registers)
 constexpr int kWalkMinCtas = 3;          // register budget: 80 per thread -> 24 warps per SM (64 registers spill the streamed-leaf walk)
 constexpr int kStackCap = 8192;          // per-warp spill slab of the walk stack (HBM/L2 resident; cells only, rarely touched)
 constexpr int kStackSmem = 512;          // per-warp stack window in shared memory
