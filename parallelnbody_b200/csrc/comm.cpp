@@ -111,9 +111,10 @@ class NcclComm : public Comm {
   int all_to_all_v(const void* send, const size_t* send_bytes, const size_t* send_off, void* recv, const size_t* recv_bytes,
                    const size_t* recv_off, cudaStream_t s) override {
     // what a rank keeps for itself is a plain device copy (HBM speed), not a send / receive pair through NCCL's channels
-    if (send_bytes[rank_] && send_bytes[rank_] == recv_bytes[rank_] && (const char*)send + send_off[rank_] != (char*)recv + recv_off[rank_])
+    static const bool self_nccl = getenv("NBODY_A2A_SELF_NCCL") != nullptr;   // development knob: the own share through NCCL as well
+    const bool self_done = !self_nccl && send_bytes[rank_] == recv_bytes[rank_];
+    if (self_done && send_bytes[rank_] && (const char*)send + send_off[rank_] != (char*)recv + recv_off[rank_])
       NB_CUDA(cudaMemcpyAsync((char*)recv + recv_off[rank_], (const char*)send + send_off[rank_], send_bytes[rank_], cudaMemcpyDeviceToDevice, s));
-    const bool self_done = send_bytes[rank_] == recv_bytes[rank_];
     NB_NCCL(api()->GroupStart(), "ncclGroupStart");
     // an error inside the group must still close it, or every later NCCL call of this thread joins the open group
     ncclResult_t bad = ncclSuccess;
@@ -131,7 +132,8 @@ class NcclComm : public Comm {
 
   int all_to_all_v_multi(int nbuf, const void* const* send, void* const* recv, const size_t* elem, const size_t* send_cnt,
                          const size_t* send_off, const size_t* recv_cnt, const size_t* recv_off, cudaStream_t s) override {
-    const bool self_done = send_cnt[rank_] == recv_cnt[rank_];
+    static const bool self_nccl = getenv("NBODY_A2A_SELF_NCCL") != nullptr;
+    const bool self_done = !self_nccl && send_cnt[rank_] == recv_cnt[rank_];
     if (self_done && send_cnt[rank_])
       for (int k = 0; k < nbuf; k++)
         NB_CUDA(cudaMemcpyAsync((char*)recv[k] + recv_off[rank_] * elem[k], (const char*)send[k] + send_off[rank_] * elem[k], send_cnt[rank_] * elem[k],
