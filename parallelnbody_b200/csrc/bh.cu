@@ -466,13 +466,15 @@ monopole_kernel(const float4* __restrict__ posm, const int2* __restrict__ range,
 // entries per round, one per lane; each lane tests its cell against the GROUP's bounding box:
 //     accept  <=>  half-width / dmin < theta,  dmin = distance(box, cell COM)          (cf. Size / d < Theta, h:103)
 // dmin <= every member's own d, so an accepted cell is one the reference would accept for each member. Accepted cells
-// and the bodies of opened leaves are appended to a 64-entry ring in shared memory; whenever 32 are pending, all lanes
-// evaluate them against their bodies with the direct-sum interaction (FP32-pipe bound, no divergence). Opened cells
+// and the bodies of opened leaves are appended to a 128-entry ring in shared memory; whenever 64 are pending, all lanes
+// evaluate them against their bodies with the direct-sum interaction (no divergence; the one evaluation site). Opened cells
 // push their children; the bodies of opened leaves never touch the stack - they are streamed through the ring 32 at a
-// time, the next chunk in flight while the current one is evaluated. The stack holds cells only: its top lives in shared
-// memory (512 entries per warp), older entries spill to a per-warp slab in global memory.
-// The pending ring is SoA (x[64] | y[64] | z[64] | m[64]) so that one LDS.128 yields four consecutive x (y, z, m) and the
+// time. The stack holds cells only: its top lives in a linear shared-memory window (768 entries per warp, plain stores
+// for the pushes), older entries spill to a per-warp slab in global memory.
+// The pending ring is SoA (x[128] | y[128] | z[128] | m[128]) so that one LDS.128 yields four consecutive x (y, z, m) and the
 // evaluation runs on PAIRS of entries with Blackwell packed fp32 (FADD2 / FFMA2 / FMUL2), as K1 does.
+// What bounds it (ncu, profiles/r2_ncu_summary_direct_and_walk.md): instruction issue shared by traversal (38 % of the
+// instructions) and evaluation; three CTAs per SM is the measured optimum (kWalkMinCtas1).
 template <int B, bool EPS0>
 __device__ __forceinline__ void eval_list(const float* __restrict__ ring, const int head, const int count, const float2 (&nx)[B],
                                           const float2 (&ny)[B], const float2 (&nz)[B], const float2 eps2,
