@@ -1175,7 +1175,11 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
       NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split_ctas, tree_split_kernel, 256, 0));
       split_ctas = std::max(1, std::min(split_ctas, 8));
     }
-    NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(sm_count() * split_ctas), dim3(256), args, 0, s));
+    // a small tree (the one over the received locally-essential points) has too few nodes per generation to occupy every
+    // block, and each extra block makes the barrier slower: 2 per SM measured 146 us against 159 us at 6 for 250k points
+    static const int small_ctas = getenv("NBODY_SPLIT_CTAS_SMALL") ? atoi(getenv("NBODY_SPLIT_CTAS_SMALL")) : 2;
+    const int ctas = n < (1 << 20) ? std::max(1, std::min(split_ctas, small_ctas)) : split_ctas;
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(sm_count() * ctas), dim3(256), args, 0, s));
   }
   if (p.node_boxes) {
     if (m->cap_boxes_nodes < m->cap_nodes) {
@@ -1798,7 +1802,8 @@ int bh_let_plan(BHState& local, Comm* comm, const BHParams& p, const float4* pos
                     &m->let_out, &m->let_cnt, &cap_let};
     int per_sm = 1;
     NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, let_export_kernel, 256, 0));
-    NB_CUDA(cudaLaunchCooperativeKernel((void*)let_export_kernel, dim3(sm_count() * std::max(1, std::min(per_sm, 4))), dim3(256), args, 0, s));
+    static const int export_ctas = getenv("NBODY_EXPORT_CTAS") ? atoi(getenv("NBODY_EXPORT_CTAS")) : 4;   // measured: 396 / 350 / 329 us at 1 / 2 / 4 per SM
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)let_export_kernel, dim3(sm_count() * std::max(1, std::min(per_sm, export_ctas))), dim3(256), args, 0, s));
     *launches += 1;
   }
   // one message per rank: [world + 1] migration offsets | [world] export counts; one all-gather, one host read
