@@ -1178,7 +1178,7 @@ int bh_build(BHState& st, const BHParams& p, const float4* posm_in, const float4
     // a small tree (the one over the received locally-essential points) has too few nodes per generation to occupy every
     // block, and each extra block makes the barrier slower: 2 per SM measured 146 us against 159 us at 6 for 250k points
     static const int small_ctas = getenv("NBODY_SPLIT_CTAS_SMALL") ? atoi(getenv("NBODY_SPLIT_CTAS_SMALL")) : 2;
-    const int ctas = n < (1 << 20) ? std::max(1, std::min(split_ctas, small_ctas)) : split_ctas;
+    const int ctas = n < 400000 ? std::max(1, std::min(split_ctas, small_ctas)) : split_ctas;
     NB_CUDA(cudaLaunchCooperativeKernel((void*)tree_split_kernel, dim3(sm_count() * ctas), dim3(256), args, 0, s));
   }
   if (p.node_boxes) {
