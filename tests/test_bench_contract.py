@@ -40,3 +40,18 @@ def test_product_arm_refuses_without_gpu():
         pytest.skip("GPU present")
     r = _run("--steps", "1", "--warmup", "0")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_roofline_traffic_comes_from_the_committed_ncu_captures():
+    """`roofline.traffic` is read from profiles/traffic.json (written by tools/ncu_traffic.py from `ncu --set full` captures),
+    never typed in: both dominant kernels have an entry, and it is at least the kernel's algorithmic bytes."""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = bench.load_traffic("direct_packed_kernel", "plummer_1m_direct")
+    w = bench.load_traffic("bh_walk_group_kernel", "plummer_1m_bh")
+    n = 1 << 20
+    assert d is not None and d >= 16.0 * n            # at least the sources once
+    assert w is not None and w >= 16.0 * n            # at least the bodies once
+    assert bench.load_traffic("no_such_kernel", "plummer_1m_direct") is None
+    src = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert "ncu --set full" in src["plummer_1m_direct"]["direct_packed_kernel__source"]
